@@ -1,0 +1,201 @@
+"""ctypes binding of ``libtraceml_b200.so`` (declared in ``include/traceml_b200.h``).
+
+This is the only place Python crosses into native code.  Loading fails loudly:
+there is no pure-Python or CPU fallback for any entry point.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Any, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtraceml_b200.so")
+
+TML_N_PHASES = 6
+TML_MAX_PHASES = 8
+TML_MAX_RANKS = 64
+TML_SERIES_PER_STEP = 16
+TML_OK = 0
+TML_ERR_CAPTURE = -7
+TML_ERR_NONMONOTONIC = -5
+KIND_TIME, KIND_MEM = 0, 1
+MASK_TIME, MASK_MEM = 1, 2
+
+u8, u32, u64, i32, i64, f64 = C.c_uint8, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_double
+vp = C.c_void_p
+
+
+class StepRecord(C.Structure):
+    _fields_ = [("step", u64), ("dur_ns", u64 * TML_N_PHASES), ("n_calls", u32 * TML_N_PHASES),
+                ("peak_alloc", u64), ("peak_resv", u64), ("host_ts", f64), ("gpu_mask", u32),
+                ("flags", u32), ("seq", u64), ("_pad", u64)]
+
+
+class ProcRecord(C.Structure):
+    _fields_ = [("seq", u64), ("ts", f64), ("cpu_pct", f64), ("rss", u64), ("mem_alloc", u64),
+                ("mem_resv", u64), ("mem_total", u64), ("flags", u32), ("cpu_cores", u32)]
+
+
+class LivePhase(C.Structure):
+    _fields_ = [("count", u64), ("sum_ns", u64), ("worst_ns", u64), ("median_ns", u64)]
+
+
+class LiveStats(C.Structure):
+    _fields_ = [("steps_committed", u64), ("phase", LivePhase * TML_MAX_PHASES)]
+
+
+class WinInfo(C.Structure):
+    _fields_ = [("n_retained", u64), ("latest_step", u64), ("monotone", u32), ("dup_rows", u32),
+                ("n_rows", u64 * 2), ("n_cand", u64 * 2), ("lo", u64 * 2), ("hi", u64 * 2),
+                ("t_sums", f64 * 7), ("t_count", u64)]
+
+
+class AlignInfo(C.Structure):
+    _fields_ = [("n_common", u64), ("start_step", u64), ("end_step", u64), ("n_rows", u64),
+                ("t_sums", f64 * 7), ("m_sums", f64 * 4)]
+
+
+class ReduceArgs(C.Structure):
+    _fields_ = [("n_ranks", u32), ("mask", u32), ("n_common", u64), ("shard_lo", u64),
+                ("shard_hi", u64), ("rows", vp * TML_MAX_RANKS), ("series", vp)]
+
+
+class BandArgs(C.Structure):
+    _fields_ = [("n_common", u64), ("shard_lo", u64), ("shard_hi", u64),
+                ("band_lo", (u64 * 3) * 2), ("band_hi", (u64 * 3) * 2), ("tail_first", u64 * 2)]
+
+
+class BandOut(C.Structure):
+    _fields_ = [("sum", (f64 * 3) * TML_SERIES_PER_STEP), ("cnt", (u64 * 3) * TML_SERIES_PER_STEP),
+                ("tail_first", f64 * TML_SERIES_PER_STEP), ("tail_last", f64 * TML_SERIES_PER_STEP)]
+
+
+class ProcAgg(C.Structure):
+    _fields_ = [("n", u64), ("n_gpu", u64), ("ts_min", f64), ("ts_max", f64),
+                ("sum_cpu", f64), ("max_cpu", f64), ("sum_rss", f64), ("max_rss", f64),
+                ("sum_used", f64), ("max_used", f64), ("sum_resv", f64), ("max_resv", f64),
+                ("max_total", f64), ("max_ratio", f64), ("max_cores", u32),
+                ("any_gpu_available", u32)]
+
+
+class RankMeans(C.Structure):
+    _fields_ = [("rank", i32), ("steps_analyzed", i64), ("dataloader_ms", f64), ("forward_ms", f64),
+                ("backward_ms", f64), ("optimizer_ms", f64), ("step_cpu_ms", f64)]
+
+
+class TrendIn(C.Structure):
+    _fields_ = [("valid", i32), ("baseline_avg", f64), ("mid_avg", f64), ("recent_avg", f64)]
+
+
+class StDiagIn(C.Structure):
+    _fields_ = [("n_ranks", i32), ("max_rows", i32), ("n_common", i64), ("completed_step", i64),
+                ("ranks", RankMeans * TML_MAX_RANKS), ("trend_step", TrendIn),
+                ("trend_wait", TrendIn), ("trend_dl", TrendIn)]
+
+
+class MemMetricIn(C.Structure):
+    _fields_ = [("n_ranks", i32), ("ranks", i32 * TML_MAX_RANKS), ("rank_peak", f64 * TML_MAX_RANKS),
+                ("trend_worst", TrendIn), ("trend_median", TrendIn), ("points", i32),
+                ("tail_first", f64), ("tail_last", f64)]
+
+
+class MemDiagIn(C.Structure):
+    _fields_ = [("steps_used", i64), ("window_size", i32), ("completed_step", i64),
+                ("ranks_seen", i32), ("gpu_total_bytes", f64), ("n_metrics", i32),
+                ("metric", MemMetricIn * 2)]
+
+
+class ProcDiagIn(C.Structure):
+    _fields_ = [("n_ranks", i32), ("ranks", i32 * TML_MAX_RANKS), ("agg", ProcAgg * TML_MAX_RANKS),
+                ("ram_total", f64 * TML_MAX_RANKS), ("gpu_count", i32 * TML_MAX_RANKS)]
+
+
+assert C.sizeof(StepRecord) == 128 and C.sizeof(ProcRecord) == 64
+
+# name -> (restype, argtypes); every symbol include/traceml_b200.h declares
+SIGNATURES = {
+    "tml_init": (C.c_int, [C.c_int, C.c_int, C.c_int, u32, u32, C.POINTER(vp)]),
+    "tml_shutdown": (C.c_int, [vp]),
+    "tml_abi_version": (u32, []),
+    "tml_last_error": (C.c_char_p, []),
+    "tml_status_str": (C.c_char_p, [C.c_int]),
+    "tml_phase_begin": (C.c_int, [vp, u32, vp]),
+    "tml_phase_end": (C.c_int, [vp, u32, C.c_int, vp]),
+    "tml_phase_host": (C.c_int, [vp, u32, u64]),
+    "tml_step_commit": (C.c_int, [vp, u64, u64, u64, u32, f64, vp]),
+    "tml_step_discard": (C.c_int, [vp]),
+    "tml_drain": (C.c_int, [vp, vp, u32, C.POINTER(u32), C.POINTER(u64)]),
+    "tml_live": (C.c_int, [vp, C.POINTER(LiveStats)]),
+    "tml_proc_commit": (C.c_int, [vp, C.POINTER(ProcRecord), vp]),
+    "tml_proc_drain": (C.c_int, [vp, vp, u32, C.POINTER(u32), C.POINTER(u64)]),
+    "tml_step_count": (u64, [vp]),
+    "tml_proc_count": (u64, [vp]),
+    "tml_ring_load": (C.c_int, [vp, vp, u64, vp]),
+    "tml_proc_load": (C.c_int, [vp, vp, u64, vp]),
+    "tml_ring_reset": (C.c_int, [vp]),
+    "tml_win_prepare": (C.c_int, [vp, u32, vp, C.POINTER(WinInfo)]),
+    "tml_win_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
+    "tml_win_select": (C.c_int, [vp, u32, u64, u64, vp, u32, vp, C.POINTER(AlignInfo)]),
+    "tml_win_rows": (vp, [vp, u32]),
+    "tml_win_rows_export": (C.c_int, [vp, u32, vp]),
+    "tml_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "tml_peer_close": (C.c_int, [vp, vp]),
+    "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),
+    "tml_win_bands": (C.c_int, [vp, vp, C.POINTER(BandArgs), vp, C.POINTER(BandOut)]),
+    "tml_proc_reduce": (C.c_int, [vp, u32, vp, C.POINTER(ProcAgg)]),
+    "tml_diag_step_time": (C.c_int, [C.POINTER(StDiagIn), C.c_char_p, C.c_size_t]),
+    "tml_diag_step_memory": (C.c_int, [C.POINTER(MemDiagIn), C.c_char_p, C.c_size_t]),
+    "tml_diag_process": (C.c_int, [C.POINTER(ProcDiagIn), C.c_char_p, C.c_size_t]),
+}
+
+_LIB: Optional[C.CDLL] = None
+
+
+class TraceMLNativeError(RuntimeError):
+    """A libtraceml_b200 call returned a negative status."""
+
+
+def lib() -> C.CDLL:
+    """Load the native library once.  Raises if it is missing or stale."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"traceml_b200: native extension not found at {LIB_PATH}. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback."
+        )
+    handle = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    ver = handle.tml_abi_version()
+    if ver != 1:
+        raise ImportError(f"traceml_b200: ABI version {ver} != 1 ({LIB_PATH} is stale)")
+    _LIB = handle
+    return handle
+
+
+def check(status: int, what: str = "") -> int:
+    if status < 0:
+        l = lib()
+        msg = (l.tml_last_error() or b"").decode("utf-8", "replace")
+        name = (l.tml_status_str(status) or b"").decode()
+        raise TraceMLNativeError(f"{what or 'libtraceml_b200'}: {name} ({status}) {msg}".strip())
+    return status
+
+
+def diag_json(fn_name: str, arg: C.Structure, cap: int = 1 << 16) -> Any:
+    """Run one of the tml_diag_* engines and parse its JSON."""
+    l = lib()
+    buf = C.create_string_buffer(cap)
+    rc = getattr(l, fn_name)(C.byref(arg), buf, cap)
+    if rc == -8:  # TML_ERR_SMALL
+        return diag_json(fn_name, arg, cap * 8)
+    check(rc, fn_name)
+    return json.loads(buf.value.decode("utf-8"))

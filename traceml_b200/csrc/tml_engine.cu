@@ -1,0 +1,1567 @@
+// tml_engine.cu -- kernels + C-ABI of the B200-native telemetry engine (sm_100a).
+//
+// Kernel map:
+//   K1  k_stamp_begin / k_stamp_end   %globaltimer phase stamps on the training stream
+//   K2  k_commit                      in-flight record -> smem -> one 128-B line in the
+//                                     HBM ring (+ host-mapped mirror), running stats
+//   K5  k_proc_commit                 64-B process sample into the proc ring
+//   K3a k_window_rows                 ring -> WindowRow[] (ns->ms), step ids, flags, bounds
+//   K3b k_presence                    presence bytes over [glo, glo+span)
+//   K3c k_sel_count/k_sel_scan/k_sel_scatter   suffix-select of the last W common steps
+//   K3d k_gather                      dense aligned rows + per-rank sums
+//   K4  k_window_reduce<R>            per-step cross-rank median/max, 16 series
+//   K4b k_bands                       trend band sums
+//   K6  k_proc_reduce                 per-rank process aggregates
+//
+// Nothing here is a dense contraction: no tensor-core path.  Every bulk kernel
+// is HBM-bound; accesses are 16-byte vectorised and warp-coalesced, tiles are
+// staged through swizzled shared memory where the record layout (AoS, 128 B)
+// would otherwise make a warp touch 32 lines per load.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/traceml_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+static_assert(sizeof(tml_step_record) == 128, "StepRecord must be 128 B");
+static_assert(sizeof(tml_window_row) == 64, "WindowRow must be 64 B");
+static_assert(sizeof(tml_proc_record) == 64, "ProcRecord must be 64 B");
+
+#define TML_N_SLOTS 64u      // begin-timestamp slots (regions in flight)
+#define TML_N_EPOCHS 8u      // in-flight accumulator sets (steps in flight)
+#define TML_MEMSTAT_SLOTS 4096u
+#define TML_HIST_BINS 256u
+
+// row flags written by k_window_rows
+#define RF_USABLE 1u       // some summarised phase > 0  (model.py:188-196)
+#define RF_HAS_MEM 2u
+#define RF_IN_TIME 4u      // inside the last-W time window
+#define RF_CAND_T 8u       // time-alignment candidate: usable, in window, first row of its step id
+#define RF_CAND_M 16u      // memory candidate: has_mem and last row of its step id
+
+// ------------------------------------------------------------------ device state
+
+struct DevAcc {
+  u64 dur_ns[TML_MAX_PHASES];
+  u32 n_calls[TML_MAX_PHASES];
+  u32 gpu_mask;
+  u32 _pad;
+};
+
+struct DevState {
+  u64 begin_ts[TML_N_SLOTS];
+  DevAcc acc[TML_N_EPOCHS];
+  u64 head;       // step records committed
+  u64 proc_head;  // proc records committed
+  u64 live_sum[TML_MAX_PHASES];
+  u64 live_max[TML_MAX_PHASES];
+  u32 hist[TML_N_PHASES][TML_HIST_BINS];
+};
+
+// host-mapped page: written by kernels, read by the sampler thread with no CUDA call
+struct HostPage {
+  volatile u64 mirror_head;
+  volatile u64 pmirror_head;
+  tml_live_stats live;
+  u64 memstat[TML_MEMSTAT_SLOTS][2];  // allocator peak counters, written by the host at commit
+};
+
+struct CommitArgs {
+  u64 step;
+  double host_ts;
+  u64 host_dur[TML_MAX_PHASES];
+  u32 host_calls[TML_MAX_PHASES];
+  u32 epoch;
+  u32 flags;
+  u32 memslot;
+  u32 _pad;
+};
+
+struct WinAcc {  // integer side results of k_window_rows (atomics; order-independent)
+  u64 lo[2];
+  u64 hi[2];
+  u64 ncand[2];
+  u64 nrows[2];
+  u64 latest_step;
+  u64 violations;
+  u64 dups;
+  u64 t_count;
+};
+
+// ------------------------------------------------------------------ device helpers
+
+__device__ __forceinline__ u64 globaltimer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+__device__ __forceinline__ double shfl_idx_f64(double v, int src, int width) {
+  return __shfl_sync(0xffffffffu, v, src, width);
+}
+
+// log-linear histogram bin of a duration: 8 sub-bins per octave, 2^0 .. 2^32 ns
+__device__ __forceinline__ u32 hist_bin(u64 ns) {
+  if (ns < 8ull) return (u32)ns;
+  if (ns >> 32) return TML_HIST_BINS - 1u;
+  int msb = 63 - __clzll((long long)ns);  // >= 3
+  u32 sub = (u32)((ns >> (msb - 3)) & 7ull);
+  return (u32)(msb << 3) | sub;  // msb in [3,31] -> bins 24..255
+}
+__device__ __forceinline__ u64 hist_bin_center(u32 bin) {
+  if (bin < 8u) return (u64)bin;
+  u32 msb = bin >> 3, sub = bin & 7u;
+  u64 lo = (1ull << msb) + ((u64)sub << (msb - 3));
+  return lo + ((1ull << (msb - 3)) >> 1);
+}
+
+// ------------------------------------------------------------------ K1: stamps
+
+__global__ void k_stamp_begin(DevState* st, u32 slot) {
+  if (threadIdx.x == 0) st->begin_ts[slot] = globaltimer_ns();
+}
+
+__global__ void k_stamp_end(DevState* st, u32 slot, u32 phase, u32 epoch) {
+  if (threadIdx.x == 0) {
+    u64 t1 = globaltimer_ns();
+    u64 t0 = st->begin_ts[slot];
+    u64 d = (t1 > t0) ? (t1 - t0) : 0ull;
+    DevAcc* a = &st->acc[epoch];
+    atomicAdd(&a->dur_ns[phase], d);
+    atomicAdd(&a->n_calls[phase], 1u);
+    atomicOr(&a->gpu_mask, 1u << phase);
+  }
+}
+
+// ------------------------------------------------------------------ K2: commit
+// 6 warps: warp p owns phase p's running statistics; warp 0 also assembles the
+// 128-B record in shared memory and writes it as 8 x 16-B coalesced stores.
+
+__global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* ring, u32 ring_slots,
+                                                 tml_step_record* mirror, u32 mirror_slots,
+                                                 HostPage* page, CommitArgs a) {
+  __shared__ __align__(16) u64 rec[16];
+  __shared__ u64 s_dur[TML_MAX_PHASES];
+  __shared__ u32 s_calls[TML_MAX_PHASES];
+  __shared__ u32 s_mask;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DevAcc* acc = &st->acc[a.epoch];
+
+  u64 dur = 0;
+  u32 calls = 0;
+  if (lane == 0) {
+    dur = acc->dur_ns[warp] + a.host_dur[warp];
+    calls = acc->n_calls[warp] + a.host_calls[warp];
+    s_dur[warp] = dur;
+    s_calls[warp] = calls;
+    acc->dur_ns[warp] = 0;
+    acc->n_calls[warp] = 0;
+    if (warp == 0) {
+      s_mask = acc->gpu_mask;
+      acc->gpu_mask = 0;
+      // spare accumulator slots ("other" regions) are reset, not recorded
+      acc->dur_ns[6] = 0; acc->dur_ns[7] = 0; acc->n_calls[6] = 0; acc->n_calls[7] = 0;
+    }
+  }
+  dur = __shfl_sync(0xffffffffu, dur, 0);
+  calls = __shfl_sync(0xffffffffu, calls, 0);
+
+  // running statistics of phase `warp`: count / sum / worst exactly, median from
+  // the log histogram by a warp-shuffle inclusive scan of per-lane bin counts.
+  if (calls > 0u) {
+    u32* h = st->hist[warp];
+    if (lane == 0) h[hist_bin(dur)] += 1u;
+    __syncwarp();
+    u32 c[8];
+    u32 local = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; local += c[k]; }
+    u32 incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      u32 n = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += n;
+    }
+    u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    u32 target = (total + 1u) >> 1;
+    u32 excl = incl - local;
+    unsigned hit = __ballot_sync(0xffffffffu, (excl < target) && (target <= incl));
+    int src = __ffs(hit) - 1;
+    u64 med = 0;
+    if (lane == src) {
+      u32 run = excl;
+      u32 bin = lane * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        run += c[k];
+        if (run >= target) { bin = lane * 8 + k; break; }
+      }
+      med = hist_bin_center(bin);
+      u64 sum = st->live_sum[warp] + dur;
+      u64 mx = st->live_max[warp];
+      mx = dur > mx ? dur : mx;
+      st->live_sum[warp] = sum;
+      st->live_max[warp] = mx;
+      tml_live_phase* lp = &page->live.phase[warp];
+      lp->count = total;
+      lp->sum_ns = sum;
+      lp->worst_ns = mx;
+      lp->median_ns = med;
+    }
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    u64 seq = 0;
+    if (lane == 0) {
+      seq = st->head;
+      const u64* ms = page->memstat[a.memslot];
+      u64 peak_alloc = ((const volatile u64*)ms)[0];
+      u64 peak_resv = ((const volatile u64*)ms)[1];
+      rec[0] = a.step;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) rec[1 + p] = s_dur[p];
+      rec[7] = (u64)s_calls[0] | ((u64)s_calls[1] << 32);
+      rec[8] = (u64)s_calls[2] | ((u64)s_calls[3] << 32);
+      rec[9] = (u64)s_calls[4] | ((u64)s_calls[5] << 32);
+      rec[10] = peak_alloc;
+      rec[11] = peak_resv;
+      rec[12] = (u64)__double_as_longlong(a.host_ts);
+      rec[13] = (u64)s_mask | ((u64)a.flags << 32);
+      rec[14] = seq;
+      rec[15] = 0;
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    __syncwarp();
+    if (lane < 8) {
+      uint4 v = reinterpret_cast<const uint4*>(rec)[lane];
+      reinterpret_cast<uint4*>(&ring[seq % ring_slots])[lane] = v;
+      reinterpret_cast<uint4*>(&mirror[seq % mirror_slots])[lane] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_system();
+      st->head = seq + 1;
+      page->live.steps_committed = seq + 1;
+      page->mirror_head = seq + 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K5: proc commit
+
+__global__ void k_proc_commit(DevState* st, tml_proc_record* ring, u32 slots,
+                              tml_proc_record* mirror, u32 mirror_slots, HostPage* page,
+                              tml_proc_record r) {
+  __shared__ __align__(16) tml_proc_record s;
+  const int lane = threadIdx.x;
+  u64 seq = 0;
+  if (lane == 0) { s = r; seq = st->proc_head; }
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  __syncwarp();
+  if (lane < 4) {
+    uint4 v = reinterpret_cast<const uint4*>(&s)[lane];
+    reinterpret_cast<uint4*>(&ring[seq % slots])[lane] = v;
+    reinterpret_cast<uint4*>(&mirror[seq % mirror_slots])[lane] = v;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();
+    st->proc_head = seq + 1;
+    page->pmirror_head = seq + 1;
+  }
+}
+
+// ------------------------------------------------------------------ reductions
+
+// Deterministic block sum of NV values per thread -> out[NV] (thread 0 writes).
+template <int NV, int NTHREADS>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* out) {
+  __shared__ double s_part[NTHREADS / 32][NV];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) x += shfl_xor_f64(x, m);
+    if (lane == 0) s_part[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < NTHREADS / 32; ++w) x += s_part[w][threadIdx.x];
+    out[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
+// out[c] = reduce over b of partials[b * ncols + c]; op per column: 0 sum, 1 max.
+__global__ void k_finalize(const double* partials, int nblk, int ncols, u32 max_mask, double* out) {
+  int c = threadIdx.x;
+  if (c >= ncols) return;
+  bool is_max = (max_mask >> c) & 1u;
+  double x = is_max ? -INFINITY : 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    double p = partials[(size_t)b * ncols + c];
+    x = is_max ? fmax(x, p) : (x + p);
+  }
+  out[c] = x;
+}
+
+// ------------------------------------------------------------------ K3a: window rows
+// Persistent grid; each iteration converts a 256-record tile.  The tile is
+// loaded with fully coalesced 16-B loads into XOR-swizzled shared memory so
+// the per-thread 128-B record read is bank-conflict-free, and rows leave
+// through a second swizzled buffer as coalesced 16-B stores.
+
+#define WR_THREADS 256
+
+__global__ void __launch_bounds__(WR_THREADS) k_window_rows(
+    const tml_step_record* __restrict__ ring, u32 ring_slots, u64 first_k, u64 n, u64 t_start,
+    tml_window_row* __restrict__ rows, u64* __restrict__ steps, u8* __restrict__ flags,
+    WinAcc* acc, double* partials) {
+  __shared__ uint4 s_in[WR_THREADS * 8];   // 32 KB
+  uint4* const s_out = s_in;               // rows leave through the same buffer (16 KB used)
+  __shared__ u64 s_steps[WR_THREADS + 2];
+  __shared__ u8 s_hasmem[WR_THREADS + 2];
+  __shared__ u64 s_lo[2], s_hi[2], s_ncand[2], s_nrows[2], s_latest, s_viol, s_dups, s_tcount;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_lo[0] = s_lo[1] = ~0ull; s_hi[0] = s_hi[1] = 0ull;
+    s_ncand[0] = s_ncand[1] = 0ull; s_nrows[0] = s_nrows[1] = 0ull;
+    s_latest = 0ull; s_viol = 0ull; s_dups = 0ull; s_tcount = 0ull;
+  }
+  double sums[7] = {0, 0, 0, 0, 0, 0, 0};
+  const u64 ntiles = (n + WR_THREADS - 1) / WR_THREADS;
+  const uint4* ring4 = reinterpret_cast<const uint4*>(ring);
+
+  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const u64 base = tile * WR_THREADS;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      int idx = c * WR_THREADS + tid;
+      int r = idx >> 3, q = idx & 7;
+      u64 i = base + (u64)r;
+      if (i < n) {
+        u64 slot = (first_k + i) % ring_slots;
+        s_in[r * 8 + (q ^ (r & 7))] = __ldg(&ring4[slot * 8 + q]);
+      }
+    }
+    // halo step ids for first/last-of-step tests
+    if (tid == 0) {
+      if (base > 0) {
+        const tml_step_record* p = &ring[(first_k + base - 1) % ring_slots];
+        s_steps[0] = p->step; s_hasmem[0] = (u8)(p->flags & TML_REC_HAS_MEM);
+      }
+      if (base + WR_THREADS < n) {
+        const tml_step_record* p = &ring[(first_k + base + WR_THREADS) % ring_slots];
+        s_steps[WR_THREADS + 1] = p->step; s_hasmem[WR_THREADS + 1] = (u8)(p->flags & TML_REC_HAS_MEM);
+      }
+    }
+    __syncthreads();
+
+    const u64 i = base + (u64)tid;
+    const bool live = i < n;
+    uint4 ch[8];
+    u64 step = 0;
+    u32 rflags = 0;
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ch[q] = s_in[tid * 8 + (q ^ (tid & 7))];
+      step = (u64)ch[0].x | ((u64)ch[0].y << 32);
+      rflags = ch[6].w;
+      s_steps[tid + 1] = step;
+      s_hasmem[tid + 1] = (u8)(rflags & TML_REC_HAS_MEM);
+    }
+    __syncthreads();
+
+    if (live) {
+      const u64 d0 = (u64)ch[0].z | ((u64)ch[0].w << 32);
+      const u64 d1 = (u64)ch[1].x | ((u64)ch[1].y << 32);
+      const u64 d2 = (u64)ch[1].z | ((u64)ch[1].w << 32);
+      const u64 d3 = (u64)ch[2].x | ((u64)ch[2].y << 32);
+      const u64 d4 = (u64)ch[2].z | ((u64)ch[2].w << 32);
+      const u64 d5 = (u64)ch[3].x | ((u64)ch[3].y << 32);
+      const u64 pa = (u64)ch[5].x | ((u64)ch[5].y << 32);
+      const u64 pr = (u64)ch[5].z | ((u64)ch[5].w << 32);
+      // ns -> ms: a true IEEE division (not a multiply by 1e-6) so the value is the
+      // correctly rounded quotient, identical to Python's ns / 1e6.
+      const double dl = __ddiv_rn((double)d0, 1.0e6);
+      const double h2d = __ddiv_rn((double)d1, 1.0e6);
+      const double fwd = __ddiv_rn((double)d2, 1.0e6);
+      const double bwd = __ddiv_rn((double)d3, 1.0e6);
+      const double opt = __ddiv_rn((double)d4, 1.0e6);
+      const double wall = __ddiv_rn((double)d5, 1.0e6);
+      const bool has_mem = (rflags & TML_REC_HAS_MEM) != 0u;
+      const bool usable = (dl > 0.0) || (fwd > 0.0) || (bwd > 0.0) || (opt > 0.0) || (wall > 0.0);
+      const bool in_time = i >= t_start;
+      const bool has_prev = i > 0, has_next = (i + 1) < n;
+      const u64 prev_step = s_steps[tid];
+      const u64 next_step = s_steps[tid + 2];
+      const bool first_in_win = (i == t_start) || !has_prev || (prev_step != step);
+      const bool last_m = !has_next || (next_step != step) || (s_hasmem[tid + 2] == 0);
+      u8 f = 0;
+      if (usable) f |= RF_USABLE;
+      if (has_mem) f |= RF_HAS_MEM;
+      if (in_time) f |= RF_IN_TIME;
+      const bool cand_t = usable && in_time && first_in_win;
+      const bool cand_m = has_mem && last_m;
+      if (cand_t) f |= RF_CAND_T;
+      if (cand_m) f |= RF_CAND_M;
+      steps[i] = step;
+      flags[i] = f;
+
+      atomicMax(&s_latest, step);
+      if (has_prev && step < prev_step) atomicAdd(&s_viol, 1ull);
+      if (has_prev && step == prev_step) atomicAdd(&s_dups, 1ull);
+      if (in_time) atomicAdd(&s_nrows[0], 1ull);
+      if (has_mem) atomicAdd(&s_nrows[1], 1ull);
+      if (cand_t) { atomicMin(&s_lo[0], step); atomicMax(&s_hi[0], step); atomicAdd(&s_ncand[0], 1ull); }
+      if (cand_m) { atomicMin(&s_lo[1], step); atomicMax(&s_hi[1], step); atomicAdd(&s_ncand[1], 1ull); }
+
+      if (usable && in_time) {  // model.py:241-271, same expression order
+        const double compute = (fwd + bwd) + opt;
+        const double traced = fmax(wall, compute);
+        sums[0] += dl; sums[1] += fwd; sums[2] += bwd; sums[3] += opt;
+        sums[4] += wall; sums[5] += traced; sums[6] += dl + traced;
+        atomicAdd(&s_tcount, 1ull);
+      }
+
+      // row -> swizzled staging (4 x 16 B)
+      double2 o0 = make_double2(dl, h2d), o1 = make_double2(fwd, bwd);
+      double2 o2 = make_double2(opt, wall), o3 = make_double2((double)pa, (double)pr);
+      const int sw = (tid >> 1) & 3;
+      s_out[tid * 4 + (0 ^ sw)] = *reinterpret_cast<uint4*>(&o0);
+      s_out[tid * 4 + (1 ^ sw)] = *reinterpret_cast<uint4*>(&o1);
+      s_out[tid * 4 + (2 ^ sw)] = *reinterpret_cast<uint4*>(&o2);
+      s_out[tid * 4 + (3 ^ sw)] = *reinterpret_cast<uint4*>(&o3);
+    }
+    __syncthreads();
+    uint4* rows4 = reinterpret_cast<uint4*>(rows);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int idx = c * WR_THREADS + tid;
+      int r = idx >> 2, q = idx & 3;
+      u64 ii = base + (u64)r;
+      if (ii < n) rows4[ii * 4 + q] = s_out[r * 4 + (q ^ ((r >> 1) & 3))];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicMin(&acc->lo[0], s_lo[0]); atomicMin(&acc->lo[1], s_lo[1]);
+    atomicMax(&acc->hi[0], s_hi[0]); atomicMax(&acc->hi[1], s_hi[1]);
+    atomicAdd(&acc->ncand[0], s_ncand[0]); atomicAdd(&acc->ncand[1], s_ncand[1]);
+    atomicAdd(&acc->nrows[0], s_nrows[0]); atomicAdd(&acc->nrows[1], s_nrows[1]);
+    atomicMax(&acc->latest_step, s_latest);
+    atomicAdd(&acc->violations, s_viol);
+    atomicAdd(&acc->dups, s_dups);
+    atomicAdd(&acc->t_count, s_tcount);
+  }
+  block_sum<7, WR_THREADS>(sums, partials + (size_t)blockIdx.x * 7);
+}
+
+// ------------------------------------------------------------------ K3b: presence
+
+__global__ void k_presence(const u64* __restrict__ steps, const u8* __restrict__ flags, u64 n,
+                           u32 want, u64 glo, u64 span, u8* __restrict__ presence,
+                           u32* __restrict__ rowof) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    if (flags[i] & want) {
+      u64 s = steps[i];
+      if (s >= glo && (s - glo) < span) {
+        presence[s - glo] = 1;
+        rowof[s - glo] = (u32)i;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K3c: select
+// exclusive scan of the presence bytes in three passes; keeps the last W ones.
+
+#define SEL_THREADS 256
+#define SEL_PER_THREAD 16
+#define SEL_TILE (SEL_THREADS * SEL_PER_THREAD)
+
+__device__ __forceinline__ u32 count16(const u8* __restrict__ p, u64 base, u64 span) {
+  u32 c = 0;
+  if (base + 16 <= span && ((base & 15ull) == 0ull)) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p + base));
+    // bytes are 0/1 -> popcount of the words counts the ones
+    c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+  } else {
+    for (int k = 0; k < 16; ++k) if (base + k < span) c += (p[base + k] != 0);
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_count(const u8* __restrict__ presence, u64 span,
+                                                           u32* __restrict__ blockcnt) {
+  __shared__ u32 s_w[SEL_THREADS / 32];
+  u64 base = ((u64)blockIdx.x * SEL_THREADS + threadIdx.x) * SEL_PER_THREAD;
+  u32 c = (base < span) ? count16(presence, base, span) : 0u;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) t += s_w[w];
+    blockcnt[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of blockcnt[nb] in place, total -> *total_out
+__global__ void __launch_bounds__(1024) k_sel_scan(u32* blockcnt, u32 nb, u64* total_out) {
+  __shared__ u32 s_w[32];
+  __shared__ u32 s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (u32 base = 0; base < nb; base += 1024) {
+    u32 i = base + threadIdx.x;
+    u32 v = (i < nb) ? blockcnt[i] : 0u;
+    u32 incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      u32 w = s_w[lane];
+      u32 wi = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, wi, off);
+        if (lane >= off) wi += t;
+      }
+      s_w[lane] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    u32 carry = s_carry;
+    u32 excl = carry + s_w[warp] + (incl - v);
+    if (i < nb) blockcnt[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_w[warp] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = (u64)s_carry;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter(
+    const u8* __restrict__ presence, u64 span, const u32* __restrict__ blockoff,
+    const u64* __restrict__ total_p, u64 window, u64 glo, const u32* __restrict__ rowof,
+    u32* __restrict__ sel_rows, u64* __restrict__ sel_steps) {
+  __shared__ u32 s_w[SEL_THREADS / 32];
+  const u64 total = *total_p;
+  const u64 keep = total < window ? total : window;
+  const u64 skip = total - keep;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u64 base = ((u64)blockIdx.x * SEL_THREADS + threadIdx.x) * SEL_PER_THREAD;
+  u32 c = (base < span) ? count16(presence, base, span) : 0u;
+  u32 incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    u32 t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  u32 woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_w[w];
+  u64 rank = (u64)blockoff[blockIdx.x] + woff + (incl - c);
+  if (c == 0u) return;
+  for (int k = 0; k < SEL_PER_THREAD; ++k) {
+    u64 i = base + k;
+    if (i < span && presence[i]) {
+      if (rank >= skip) {
+        u64 j = rank - skip;
+        sel_rows[j] = rowof[i];
+        sel_steps[j] = glo + i;
+      }
+      ++rank;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K3d: gather
+// thread = (row j, 16-B chunk q).  chunk roles: q0 (dl,h2d) q1 (fwd,bwd)
+// q2 (opt,wall) q3 (alloc,resv).  Sums follow alignment.py:59-75.
+
+#define GA_THREADS 256
+
+__global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __restrict__ rows,
+                                                      const u32* __restrict__ sel_rows, u64 nsel,
+                                                      tml_window_row* __restrict__ xrows,
+                                                      double* partials /* [grid][16] */) {
+  __shared__ double s_part[GA_THREADS / 32][4][4];
+  const uint4* rows4 = reinterpret_cast<const uint4*>(rows);
+  uint4* x4 = reinterpret_cast<uint4*>(xrows);
+  const int q = threadIdx.x & 3;
+  double a0 = 0, a1 = 0, a2 = (q == 3) ? -INFINITY : 0.0, a3 = (q == 3) ? -INFINITY : 0.0;
+  const u64 nthreads = (u64)gridDim.x * GA_THREADS;
+  const u64 work = nsel * 4ull;
+  // every thread of a 4-lane group runs the same trip count (work is a multiple of 4)
+  // block-uniform trip count: the width-4 shuffles below need every lane of the warp
+  for (u64 tb = (u64)blockIdx.x * GA_THREADS; tb < work; tb += nthreads) {
+    const u64 t = tb + threadIdx.x;
+    const bool ok = t < work;
+    const u64 j = t >> 2;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ok) {
+      const u32 src = sel_rows[j];
+      v = __ldg(&rows4[(u64)src * 4 + q]);
+      x4[j * 4 + q] = v;
+    }
+    double2 d = *reinterpret_cast<double2*>(&v);
+    // q1 -> q2: fwd + bwd ; q0 -> q2: dl
+    double fb = shfl_idx_f64(d.x + d.y, 1, 4);
+    double dl = shfl_idx_f64(d.x, 0, 4);
+    if (!ok) continue;
+    if (q == 0) {
+      a0 += d.x;
+    } else if (q == 1) {
+      a0 += d.x; a1 += d.y;
+    } else if (q == 2) {
+      const double compute = fb + d.x;         // (fwd + bwd) + opt
+      const double traced = fmax(d.y, compute);
+      a0 += d.x;                               // opt
+      a1 += fmax(0.0, traced);                 // aligned step_cpu (alignment.py:72)
+      a2 += traced;
+      a3 += dl + traced;
+    } else {
+      a0 += d.x; a1 += d.y;
+      a2 = fmax(a2, d.x); a3 = fmax(a3, d.y);
+    }
+  }
+  // reduce over lanes of the same chunk class (xor 4, 8, 16 keeps q)
+  const bool is_max = (q == 3);
+#pragma unroll
+  for (int m = 4; m <= 16; m <<= 1) {
+    a0 += shfl_xor_f64(a0, m);
+    a1 += shfl_xor_f64(a1, m);
+    double b2 = shfl_xor_f64(a2, m), b3 = shfl_xor_f64(a3, m);
+    a2 = is_max ? fmax(a2, b2) : (a2 + b2);
+    a3 = is_max ? fmax(a3, b3) : (a3 + b3);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) {
+    s_part[warp][lane][0] = a0; s_part[warp][lane][1] = a1;
+    s_part[warp][lane][2] = a2; s_part[warp][lane][3] = a3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int qq = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const bool mx = (qq == 3) && (k >= 2);
+    double x = mx ? -INFINITY : 0.0;
+    for (int w = 0; w < GA_THREADS / 32; ++w) {
+      double p = s_part[w][qq][k];
+      x = mx ? fmax(x, p) : (x + p);
+    }
+    partials[(size_t)blockIdx.x * 16 + threadIdx.x] = x;
+  }
+}
+
+// ------------------------------------------------------------------ K4: window reduce
+
+template <int R>
+__device__ __forceinline__ void sort_small(double (&v)[R]) {
+  // odd-even transposition network, fully unrolled: R values in registers
+#pragma unroll
+  for (int pass = 0; pass < R; ++pass) {
+#pragma unroll
+    for (int i = (pass & 1); i + 1 < R; i += 2) {
+      double lo = fmin(v[i], v[i + 1]), hi = fmax(v[i], v[i + 1]);
+      v[i] = lo; v[i + 1] = hi;
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void median_max(double (&v)[R], double& med, double& mx) {
+  sort_small<R>(v);
+  mx = v[R - 1];
+  if (R & 1) med = v[R / 2];
+  else med = (v[(R / 2 > 0 ? R / 2 : 1) - 1] + v[R / 2]) * 0.5;  // np.median / model.py:130-138
+}
+
+struct ReduceParams {
+  const uint4* rows[TML_MAX_RANKS];
+  double* series;
+  u64 n_common, shard_lo, shard_hi;
+  u32 mask;
+  u32 n_ranks;
+};
+
+#define RD_THREADS 256
+
+template <int R>
+__global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_constant__ ReduceParams p) {
+  const int q = threadIdx.x & 3;
+  const u64 nthreads = (u64)gridDim.x * RD_THREADS;
+  const u64 work = (p.shard_hi - p.shard_lo) * 4ull;
+  const u64 n = p.n_common;
+  double* __restrict__ S = p.series;
+  const bool do_time = (p.mask & TML_MASK_TIME) != 0u, do_mem = (p.mask & TML_MASK_MEM) != 0u;
+  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads) {
+    const u64 t = tb + threadIdx.x;
+    const bool ok = t < work;  // block-uniform trip count keeps the shuffles full-warp
+    const u64 j = p.shard_lo + (t >> 2);
+    double x[R], y[R];
+    // R independent 16-B loads in flight per thread (local HBM or NVLink peer)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) v = __ldg(&p.rows[r][j * 4 + q]);
+      double2 d = *reinterpret_cast<double2*>(&v);
+      x[r] = d.x; y[r] = d.y;
+    }
+    double z[R];  // q2: wait_proxy
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double fb = shfl_idx_f64(x[r] + y[r], 1, 4);   // fwd + bwd from q1
+      if (q == 2) {
+        const double compute = fb + x[r];            // (fwd + bwd) + opt
+        const double traced = fmax(y[r], compute);   // model.py:246
+        z[r] = fmax(0.0, traced - compute);          // model.py:247
+        y[r] = traced;
+      } else {
+        z[r] = 0.0;
+      }
+    }
+    if (!ok) continue;
+    double med, mx;
+    if (q == 0) {
+      if (do_time) { median_max<R>(x, med, mx); S[0 * n + j] = med; S[1 * n + j] = mx; }
+    } else if (q == 1) {
+      if (do_time) {
+        median_max<R>(x, med, mx); S[2 * n + j] = med; S[3 * n + j] = mx;
+        median_max<R>(y, med, mx); S[4 * n + j] = med; S[5 * n + j] = mx;
+      }
+    } else if (q == 2) {
+      if (do_time) {
+        median_max<R>(x, med, mx); S[6 * n + j] = med; S[7 * n + j] = mx;
+        median_max<R>(y, med, mx); S[8 * n + j] = med; S[9 * n + j] = mx;
+        median_max<R>(z, med, mx); S[10 * n + j] = med; S[11 * n + j] = mx;
+      }
+    } else {
+      if (do_mem) {
+        median_max<R>(x, med, mx); S[12 * n + j] = med; S[13 * n + j] = mx;
+        median_max<R>(y, med, mx); S[14 * n + j] = med; S[15 * n + j] = mx;
+      }
+    }
+  }
+}
+
+// generic rank count (9..64): values in local memory, insertion sort
+__global__ void __launch_bounds__(RD_THREADS) k_window_reduce_any(const __grid_constant__ ReduceParams p) {
+  const int q = threadIdx.x & 3;
+  const int R = (int)p.n_ranks;
+  const u64 nthreads = (u64)gridDim.x * RD_THREADS;
+  const u64 work = (p.shard_hi - p.shard_lo) * 4ull;
+  const u64 n = p.n_common;
+  double* __restrict__ S = p.series;
+  const bool do_time = (p.mask & TML_MASK_TIME) != 0u, do_mem = (p.mask & TML_MASK_MEM) != 0u;
+  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads) {
+    const u64 t = tb + threadIdx.x;
+    const bool ok = t < work;
+    const u64 j = p.shard_lo + (t >> 2);
+    double x[TML_MAX_RANKS], y[TML_MAX_RANKS], z[TML_MAX_RANKS];
+    for (int r = 0; r < R; ++r) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) v = __ldg(&p.rows[r][j * 4 + q]);
+      double2 d = *reinterpret_cast<double2*>(&v);
+      x[r] = d.x; y[r] = d.y;
+      double fb = shfl_idx_f64(d.x + d.y, 1, 4);
+      if (q == 2) {
+        const double compute = fb + d.x;
+        const double traced = fmax(d.y, compute);
+        z[r] = fmax(0.0, traced - compute);
+        y[r] = traced;
+      } else {
+        z[r] = 0.0;
+      }
+    }
+    if (!ok) continue;
+    auto mm = [&](double* v, double& med, double& mx) {
+      for (int a = 1; a < R; ++a) {
+        double key = v[a];
+        int b = a - 1;
+        while (b >= 0 && v[b] > key) { v[b + 1] = v[b]; --b; }
+        v[b + 1] = key;
+      }
+      mx = v[R - 1];
+      med = (R & 1) ? v[R / 2] : (v[R / 2 - 1] + v[R / 2]) * 0.5;
+    };
+    double med, mx;
+    const bool tq = do_time && q < 3, mq = do_mem && q == 3;
+    const int s0 = (q == 0) ? 0 : (q == 1) ? 2 : (q == 2) ? 6 : 12;
+    if ((tq && q == 0)) { mm(x, med, mx); S[0 * n + j] = med; S[1 * n + j] = mx; }
+    if ((tq && q >= 1) || mq) {
+      mm(x, med, mx); S[(u64)s0 * n + j] = med; S[(u64)(s0 + 1) * n + j] = mx;
+      mm(y, med, mx); S[(u64)(s0 + 2) * n + j] = med; S[(u64)(s0 + 3) * n + j] = mx;
+    }
+    if (tq && q == 2) { mm(z, med, mx); S[10 * n + j] = med; S[11 * n + j] = mx; }
+  }
+}
+
+// ------------------------------------------------------------------ K4b: bands
+
+struct BandParams {
+  const double* series;
+  u64 n_common, shard_lo, shard_hi;
+  u64 lo[2][3], hi[2][3];
+  u64 tail_first[2];
+};
+
+// grid (16 series, 4): y = 0..2 band sums over band ^ shard, y = 3 tail endpoints
+__global__ void __launch_bounds__(256) k_bands(const __grid_constant__ BandParams p, double* out_sum,
+                                               u64* out_cnt, double* out_tail) {
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int kind = (s >= 12) ? 1 : 0;
+  const double* v = p.series + (u64)s * p.n_common;
+  if (b == 3) {
+    if (threadIdx.x == 0) {
+      u64 f = p.tail_first[kind], l = p.n_common ? p.n_common - 1 : 0;
+      out_tail[s * 2 + 0] = (p.n_common && f >= p.shard_lo && f < p.shard_hi) ? v[f] : NAN;
+      out_tail[s * 2 + 1] = (p.n_common && l >= p.shard_lo && l < p.shard_hi) ? v[l] : NAN;
+    }
+    return;
+  }
+  u64 lo = p.lo[kind][b], hi = p.hi[kind][b];
+  if (lo < p.shard_lo) lo = p.shard_lo;
+  if (hi > p.shard_hi) hi = p.shard_hi;
+  double acc[1] = {0.0};
+  for (u64 i = lo + threadIdx.x; i < hi; i += 256) acc[0] += v[i];
+  double r[1];
+  block_sum<1, 256>(acc, r);
+  if (threadIdx.x == 0) {
+    out_sum[s * 3 + b] = r[0];
+    out_cnt[s * 3 + b] = (hi > lo) ? (hi - lo) : 0ull;
+  }
+}
+
+// ------------------------------------------------------------------ K6: proc reduce
+// columns: 0 sum_cpu 1 sum_rss 2 sum_used 3 sum_resv | max: 4 cpu 5 rss 6 used 7 resv
+// 8 total 9 ratio 10 ts_max 11 -ts_min 12 cores 13 gpu_available | 14 n_gpu (sum)
+
+#define PR_THREADS 256
+#define PR_COLS 15
+#define PR_MAXMASK (((1u << 14) - 1u) & ~0xFu)
+
+__global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_record* __restrict__ ring,
+                                                           u32 slots, u64 first_k, u64 n,
+                                                           double* partials) {
+  __shared__ double s_part[PR_THREADS / 32][PR_COLS];
+  double a[PR_COLS];
+#pragma unroll
+  for (int k = 0; k < PR_COLS; ++k) a[k] = ((PR_MAXMASK >> k) & 1u) ? -INFINITY : 0.0;
+  for (u64 i = (u64)blockIdx.x * PR_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * PR_THREADS) {
+    const uint4* p = reinterpret_cast<const uint4*>(&ring[(first_k + i) % slots]);
+    uint4 c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2), c3 = __ldg(p + 3);
+    const double ts = __longlong_as_double((long long)((u64)c0.z | ((u64)c0.w << 32)));
+    const double cpu = __longlong_as_double((long long)((u64)c1.x | ((u64)c1.y << 32)));
+    const double rss = (double)((u64)c1.z | ((u64)c1.w << 32));
+    const double used = (double)((u64)c2.x | ((u64)c2.y << 32));
+    const double resv = (double)((u64)c2.z | ((u64)c2.w << 32));
+    const double total = (double)((u64)c3.x | ((u64)c3.y << 32));
+    const u32 fl = c3.z, cores = c3.w;
+    a[0] += cpu; a[4] = fmax(a[4], cpu);
+    a[1] += rss; a[5] = fmax(a[5], rss);
+    a[10] = fmax(a[10], ts); a[11] = fmax(a[11], -ts);
+    a[12] = fmax(a[12], (double)cores);
+    a[13] = fmax(a[13], (fl & TML_PROC_GPU_AVAILABLE) ? 1.0 : 0.0);
+    if (fl & TML_PROC_HAS_GPU_METRICS) {
+      a[2] += used; a[6] = fmax(a[6], used);
+      a[3] += resv; a[7] = fmax(a[7], resv);
+      a[8] = fmax(a[8], total);
+      if (used > 0.0) a[9] = fmax(a[9], resv / used);  // loader.py:174-182
+      a[14] += 1.0;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < PR_COLS; ++k) {
+    const bool mx = (PR_MAXMASK >> k) & 1u;
+    double x = a[k];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      double y = shfl_xor_f64(x, m);
+      x = mx ? fmax(x, y) : (x + y);
+    }
+    if (lane == 0) s_part[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < PR_COLS) {
+    const bool mx = (PR_MAXMASK >> threadIdx.x) & 1u;
+    double x = mx ? -INFINITY : 0.0;
+    for (int w = 0; w < PR_THREADS / 32; ++w) {
+      double y = s_part[w][threadIdx.x];
+      x = mx ? fmax(x, y) : (x + y);
+    }
+    partials[(size_t)blockIdx.x * PR_COLS + threadIdx.x] = x;
+  }
+}
+
+// =================================================================== host side
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return set_err(TML_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                \
+  } while (0)
+
+struct tml_ctx {
+  int device = 0, rank = 0, world = 1;
+  int n_sms = 148;
+  u32 ring_slots = 0, proc_slots = 0, mirror_slots = 0, pmirror_slots = 0;
+  DevState* d_state = nullptr;
+  tml_step_record* d_ring = nullptr;
+  tml_proc_record* d_pring = nullptr;
+  HostPage* h_page = nullptr;        HostPage* d_page = nullptr;
+  tml_step_record* h_mirror = nullptr; tml_step_record* d_mirror = nullptr;
+  tml_proc_record* h_pmirror = nullptr; tml_proc_record* d_pmirror = nullptr;
+  // host-side step state (training thread)
+  u64 commits = 0;
+  u32 next_slot = 0;
+  u64 host_dur[TML_MAX_PHASES] = {0};
+  u32 host_calls[TML_MAX_PHASES] = {0};
+  // sampler-thread state
+  std::atomic<u64> proc_commits{0};
+  u64 drain_tail = 0, pdrain_tail = 0;
+  std::mutex proc_mu;
+  // reduce workspace
+  u64 cap_rows = 0;
+  tml_window_row* d_rows = nullptr;
+  u64* d_steps = nullptr;
+  u8* d_flags = nullptr;
+  u64 win_n = 0, win_tstart = 0;
+  u64 win_ncand[2] = {0, 0};
+  bool win_ready = false;
+  u64 cap_span[2] = {0, 0};
+  u32* d_rowof[2] = {nullptr, nullptr};
+  u64 cap_x[2] = {0, 0};
+  tml_window_row* d_xrows[2] = {nullptr, nullptr};
+  u64 n_common[2] = {0, 0};
+  u64 cap_sel = 0;
+  u32* d_selrow = nullptr;
+  u64* d_selstep = nullptr;
+  u64 cap_blk = 0;
+  u32* d_blockcnt = nullptr;
+  u64* d_total = nullptr;
+  WinAcc* d_winacc = nullptr;
+  double* d_partials = nullptr;  // max(grid) * 16 doubles
+  double* d_final = nullptr;     // 64 doubles
+  u64* d_bandcnt = nullptr;
+  void* h_stage = nullptr;       // pinned 4 KB result staging
+  std::unordered_map<std::string, void*> peers;
+};
+
+static int grid_for(const tml_ctx* c, u64 work_items, int per_block) {
+  u64 need = (work_items + per_block - 1) / per_block;
+  u64 cap = (u64)c->n_sms * 4ull;  // persistent-style: a multiple of the SM count
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+extern "C" {
+
+uint32_t tml_abi_version(void) { return TML_ABI_VERSION; }
+const char* tml_last_error(void) { return g_err; }
+const char* tml_status_str(int s) {
+  switch (s) {
+    case TML_OK: return "ok";
+    case TML_ERR_CUDA: return "cuda error";
+    case TML_ERR_ARG: return "bad argument";
+    case TML_ERR_STATE: return "bad state";
+    case TML_ERR_NOMEM: return "out of memory";
+    case TML_ERR_NONMONOTONIC: return "step ids decrease inside the ring";
+    case TML_ERR_UNSUPPORTED: return "unsupported";
+    case TML_ERR_CAPTURE: return "stream is capturing";
+    case TML_ERR_SMALL: return "buffer too small";
+  }
+  return "unknown";
+}
+
+int tml_init(int device, int rank, int world, uint32_t ring_slots, uint32_t proc_slots,
+             tml_ctx** out) {
+  if (!out || ring_slots == 0) return set_err(TML_ERR_ARG, "tml_init: bad arguments");
+  if (proc_slots == 0) proc_slots = 1;
+  CK(cudaSetDevice(device));
+  tml_ctx* c = new (std::nothrow) tml_ctx();
+  if (!c) return set_err(TML_ERR_NOMEM, "tml_init: host allocation failed");
+  c->device = device; c->rank = rank; c->world = world;
+  c->ring_slots = ring_slots; c->proc_slots = proc_slots;
+  c->mirror_slots = ring_slots < 8192u ? ring_slots : 8192u;
+  c->pmirror_slots = proc_slots < 16384u ? proc_slots : 16384u;
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  c->n_sms = sms > 0 ? sms : 148;
+  CK(cudaMalloc(&c->d_state, sizeof(DevState)));
+  CK(cudaMemset(c->d_state, 0, sizeof(DevState)));
+  CK(cudaMalloc(&c->d_ring, (size_t)ring_slots * sizeof(tml_step_record)));
+  CK(cudaMalloc(&c->d_pring, (size_t)proc_slots * sizeof(tml_proc_record)));
+  CK(cudaHostAlloc(&c->h_page, sizeof(HostPage), cudaHostAllocMapped));
+  memset(c->h_page, 0, sizeof(HostPage));
+  CK(cudaHostGetDevicePointer((void**)&c->d_page, c->h_page, 0));
+  CK(cudaHostAlloc(&c->h_mirror, (size_t)c->mirror_slots * sizeof(tml_step_record), cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void**)&c->d_mirror, c->h_mirror, 0));
+  CK(cudaHostAlloc(&c->h_pmirror, (size_t)c->pmirror_slots * sizeof(tml_proc_record), cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void**)&c->d_pmirror, c->h_pmirror, 0));
+  CK(cudaMalloc(&c->d_winacc, sizeof(WinAcc)));
+  CK(cudaMalloc(&c->d_total, sizeof(u64)));
+  CK(cudaMalloc(&c->d_partials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
+  CK(cudaMalloc(&c->d_final, 64 * sizeof(double)));
+  CK(cudaMalloc(&c->d_bandcnt, 64 * sizeof(u64)));
+  CK(cudaHostAlloc(&c->h_stage, 4096, cudaHostAllocDefault));
+  *out = c;
+  return TML_OK;
+}
+
+int tml_shutdown(tml_ctx* c) {
+  if (!c) return TML_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->peers) cudaIpcCloseMemHandle(kv.second);
+  cudaFree(c->d_state); cudaFree(c->d_ring); cudaFree(c->d_pring);
+  cudaFreeHost(c->h_page); cudaFreeHost(c->h_mirror); cudaFreeHost(c->h_pmirror);
+  cudaFree(c->d_rows); cudaFree(c->d_steps); cudaFree(c->d_flags);
+  for (int k = 0; k < 2; ++k) { cudaFree(c->d_rowof[k]); cudaFree(c->d_xrows[k]); }
+  cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
+  cudaFree(c->d_winacc); cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
+  cudaFreeHost(c->h_stage);
+  delete c;
+  return TML_OK;
+}
+
+// ---------------------------------------------------------------- step path
+
+static inline int check_capture(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+int tml_phase_begin(tml_ctx* c, uint32_t phase, void* stream) {
+  if (!c || phase >= TML_MAX_PHASES) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_capture(s)) return TML_ERR_CAPTURE;
+  u32 slot = c->next_slot;
+  c->next_slot = (slot + 1u) % TML_N_SLOTS;
+  k_stamp_begin<<<1, 32, 0, s>>>(c->d_state, slot);
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return set_err(TML_ERR_CUDA, "stamp_begin launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return (int)slot;
+}
+
+int tml_phase_end(tml_ctx* c, uint32_t phase, int slot, void* stream) {
+  if (!c || phase >= TML_MAX_PHASES || slot < 0 || slot >= (int)TML_N_SLOTS) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_capture(s)) return TML_ERR_CAPTURE;
+  k_stamp_end<<<1, 32, 0, s>>>(c->d_state, (u32)slot, phase, (u32)(c->commits % TML_N_EPOCHS));
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return set_err(TML_ERR_CUDA, "stamp_end launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return TML_OK;
+}
+
+int tml_phase_host(tml_ctx* c, uint32_t phase, uint64_t dur_ns) {
+  if (!c || phase >= TML_MAX_PHASES) return TML_ERR_ARG;
+  c->host_dur[phase] += dur_ns;
+  c->host_calls[phase] += 1u;
+  return TML_OK;
+}
+
+int tml_step_discard(tml_ctx* c) {
+  if (!c) return TML_ERR_ARG;
+  memset(c->host_dur, 0, sizeof(c->host_dur));
+  memset(c->host_calls, 0, sizeof(c->host_calls));
+  return TML_OK;
+}
+
+int tml_step_commit(tml_ctx* c, uint64_t step, uint64_t peak_alloc, uint64_t peak_resv,
+                    uint32_t flags, double host_ts, void* stream) {
+  if (!c) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_capture(s)) return TML_ERR_CAPTURE;
+  CommitArgs a;
+  a.step = step; a.host_ts = host_ts;
+  memcpy(a.host_dur, c->host_dur, sizeof(a.host_dur));
+  memcpy(a.host_calls, c->host_calls, sizeof(a.host_calls));
+  a.epoch = (u32)(c->commits % TML_N_EPOCHS);
+  a.flags = flags;
+  a.memslot = (u32)(c->commits % TML_MEMSTAT_SLOTS);
+  a._pad = 0;
+  // allocator peak counters go through the host-mapped counter page; the kernel reads them
+  c->h_page->memstat[a.memslot][0] = peak_alloc;
+  c->h_page->memstat[a.memslot][1] = peak_resv;
+  std::atomic_thread_fence(std::memory_order_release);
+  k_commit<<<1, 192, 0, s>>>(c->d_state, c->d_ring, c->ring_slots, c->d_mirror, c->mirror_slots,
+                              c->d_page, a);
+  memset(c->host_dur, 0, sizeof(c->host_dur));
+  memset(c->host_calls, 0, sizeof(c->host_calls));
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return set_err(TML_ERR_CUDA, "commit launch: %s", cudaGetErrorString(cudaGetLastError()));
+  c->commits += 1;
+  c->win_ready = false;
+  return TML_OK;
+}
+
+uint64_t tml_step_count(tml_ctx* c) { return c ? c->commits : 0; }
+uint64_t tml_proc_count(tml_ctx* c) { return c ? c->proc_commits.load() : 0; }
+
+// ---------------------------------------------------------------- sampler side
+
+int tml_drain(tml_ctx* c, tml_step_record* out, uint32_t max_records, uint32_t* n_out,
+              uint64_t* n_dropped) {
+  if (!c || !out || !n_out) return TML_ERR_ARG;
+  u64 head = c->h_page->mirror_head;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  u64 tail = c->drain_tail, dropped = 0;
+  if (head - tail > c->mirror_slots) { dropped = head - tail - c->mirror_slots; tail = head - c->mirror_slots; }
+  u32 n = 0;
+  while (tail < head && n < max_records) {
+    memcpy(&out[n], (const void*)&c->h_mirror[tail % c->mirror_slots], sizeof(tml_step_record));
+    ++n; ++tail;
+  }
+  c->drain_tail = tail;
+  *n_out = n;
+  if (n_dropped) *n_dropped = dropped;
+  return TML_OK;
+}
+
+int tml_proc_drain(tml_ctx* c, tml_proc_record* out, uint32_t max_records, uint32_t* n_out,
+                   uint64_t* n_dropped) {
+  if (!c || !out || !n_out) return TML_ERR_ARG;
+  u64 head = c->h_page->pmirror_head;
+  std::atomic_thread_fence(std::memory_order_acquire);
+  u64 tail = c->pdrain_tail, dropped = 0;
+  if (head - tail > c->pmirror_slots) { dropped = head - tail - c->pmirror_slots; tail = head - c->pmirror_slots; }
+  u32 n = 0;
+  while (tail < head && n < max_records) {
+    memcpy(&out[n], (const void*)&c->h_pmirror[tail % c->pmirror_slots], sizeof(tml_proc_record));
+    ++n; ++tail;
+  }
+  c->pdrain_tail = tail;
+  *n_out = n;
+  if (n_dropped) *n_dropped = dropped;
+  return TML_OK;
+}
+
+int tml_live(tml_ctx* c, tml_live_stats* out) {
+  if (!c || !out) return TML_ERR_ARG;
+  memcpy(out, (const void*)&c->h_page->live, sizeof(tml_live_stats));
+  return TML_OK;
+}
+
+int tml_proc_commit(tml_ctx* c, const tml_proc_record* sample, void* stream) {
+  if (!c || !sample) return TML_ERR_ARG;
+  std::lock_guard<std::mutex> g(c->proc_mu);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_proc_commit<<<1, 32, 0, s>>>(c->d_state, c->d_pring, c->proc_slots, c->d_pmirror,
+                                  c->pmirror_slots, c->d_page, *sample);
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return set_err(TML_ERR_CUDA, "proc_commit launch: %s", cudaGetErrorString(cudaGetLastError()));
+  c->proc_commits.fetch_add(1);
+  return TML_OK;
+}
+
+static int load_span(void* d_ring, u32 slots, size_t rec_bytes, u64 start, const void* host, u64 n,
+                     cudaStream_t s) {
+  // at most two contiguous spans (ring wrap); if n > slots only the last `slots` survive
+  const char* src = (const char*)host;
+  if (n > slots) { src += (size_t)(n - slots) * rec_bytes; start += (n - slots); n = slots; }
+  u64 pos = start % slots;
+  u64 first = (pos + n <= slots) ? n : (slots - pos);
+  CK(cudaMemcpyAsync((char*)d_ring + pos * rec_bytes, src, (size_t)first * rec_bytes,
+                     cudaMemcpyHostToDevice, s));
+  if (first < n)
+    CK(cudaMemcpyAsync(d_ring, src + (size_t)first * rec_bytes, (size_t)(n - first) * rec_bytes,
+                       cudaMemcpyHostToDevice, s));
+  return TML_OK;
+}
+
+__global__ void k_set_heads(DevState* st, u64 head, u64 proc_head, int which) {
+  if (which == 0) st->head = head; else st->proc_head = proc_head;
+}
+
+int tml_ring_load(tml_ctx* c, const tml_step_record* host, uint64_t n, void* stream) {
+  if (!c || (!host && n)) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = load_span(c->d_ring, c->ring_slots, sizeof(tml_step_record), c->commits, host, n, s);
+  if (rc != TML_OK) return rc;
+  c->commits += n;
+  k_set_heads<<<1, 1, 0, s>>>(c->d_state, c->commits, 0, 0);
+  CK(cudaPeekAtLastError());
+  c->win_ready = false;
+  return TML_OK;
+}
+
+int tml_proc_load(tml_ctx* c, const tml_proc_record* host, uint64_t n, void* stream) {
+  if (!c || (!host && n)) return TML_ERR_ARG;
+  std::lock_guard<std::mutex> g(c->proc_mu);
+  cudaStream_t s = (cudaStream_t)stream;
+  u64 cur = c->proc_commits.load();
+  int rc = load_span(c->d_pring, c->proc_slots, sizeof(tml_proc_record), cur, host, n, s);
+  if (rc != TML_OK) return rc;
+  c->proc_commits.store(cur + n);
+  k_set_heads<<<1, 1, 0, s>>>(c->d_state, 0, cur + n, 1);
+  CK(cudaPeekAtLastError());
+  return TML_OK;
+}
+
+int tml_ring_reset(tml_ctx* c) {
+  if (!c) return TML_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(c->d_state, 0, sizeof(DevState)));
+  memset(c->h_page, 0, sizeof(HostPage));
+  c->commits = 0; c->proc_commits.store(0); c->next_slot = 0;
+  c->drain_tail = 0; c->pdrain_tail = 0;
+  memset(c->host_dur, 0, sizeof(c->host_dur));
+  memset(c->host_calls, 0, sizeof(c->host_calls));
+  c->win_ready = false;
+  return TML_OK;
+}
+
+// ---------------------------------------------------------------- reduce
+
+}  // extern "C"
+
+template <typename T>
+static int ensure(T** p, u64* cap, u64 need, bool exact_alloc = false) {
+  if (need <= *cap && *p) return TML_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  u64 n = need < 1 ? 1 : need;
+  if (!exact_alloc) n = n + n / 4 + 64;
+  cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) return set_err(TML_ERR_NOMEM, "cudaMalloc(%llu B): %s",
+                                       (u64)(n * sizeof(T)), cudaGetErrorString(e));
+  *cap = n;
+  return TML_OK;
+}
+
+extern "C" {
+
+int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out) {
+  if (!c || !out || window == 0) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  const u64 n = c->commits < c->ring_slots ? c->commits : c->ring_slots;
+  const u64 first_k = c->commits - n;
+  c->win_n = n;
+  c->win_tstart = n > window ? n - window : 0;
+  out->n_retained = n;
+  out->monotone = 1;
+  c->win_ncand[0] = c->win_ncand[1] = 0;
+  if (n == 0) { c->win_ready = true; return TML_OK; }
+  int rc;
+  u64 cap = c->cap_rows;
+  if (n > cap) {
+    cudaFree(c->d_rows); cudaFree(c->d_steps); cudaFree(c->d_flags);
+    c->d_rows = nullptr; c->d_steps = nullptr; c->d_flags = nullptr; c->cap_rows = 0;
+    u64 want = n + n / 4 + 64;
+    if (want > c->ring_slots) want = c->ring_slots;
+    if (want < n) want = n;
+    CK(cudaMalloc(&c->d_rows, (size_t)want * sizeof(tml_window_row)));
+    CK(cudaMalloc(&c->d_steps, (size_t)want * sizeof(u64)));
+    CK(cudaMalloc(&c->d_flags, (size_t)want));
+    c->cap_rows = want;
+  }
+  WinAcc init;
+  memset(&init, 0, sizeof(init));
+  init.lo[0] = init.lo[1] = ~0ull;
+  CK(cudaMemcpyAsync(c->d_winacc, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+  const int grid = grid_for(c, n, WR_THREADS);
+  k_window_rows<<<grid, WR_THREADS, 0, s>>>(c->d_ring, c->ring_slots, first_k, n, c->win_tstart,
+                                            c->d_rows, c->d_steps, c->d_flags, c->d_winacc,
+                                            c->d_partials);
+  CK(cudaPeekAtLastError());
+  k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, 7, 0u, c->d_final);
+  CK(cudaPeekAtLastError());
+  char* st = (char*)c->h_stage;
+  CK(cudaMemcpyAsync(st, c->d_winacc, sizeof(WinAcc), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 256, c->d_final, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  WinAcc acc;
+  memcpy(&acc, st, sizeof(acc));
+  memcpy(out->t_sums, st + 256, 7 * sizeof(double));
+  out->latest_step = acc.latest_step;
+  out->monotone = acc.violations == 0 ? 1u : 0u;
+  out->dup_rows = (u32)acc.dups;
+  for (int k = 0; k < 2; ++k) {
+    out->n_rows[k] = acc.nrows[k];
+    out->n_cand[k] = acc.ncand[k];
+    out->lo[k] = acc.ncand[k] ? acc.lo[k] : 0;
+    out->hi[k] = acc.ncand[k] ? acc.hi[k] : 0;
+  }
+  out->t_count = acc.t_count;
+  c->win_ncand[0] = acc.ncand[0]; c->win_ncand[1] = acc.ncand[1];
+  c->win_ready = true;
+  (void)rc;
+  if (!out->monotone)
+    return set_err(TML_ERR_NONMONOTONIC, "step ids decrease inside the retained ring (%llu places)",
+                   acc.violations);
+  return TML_OK;
+}
+
+int tml_win_presence(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, uint8_t* presence,
+                     void* stream) {
+  if (!c || kind > 1 || !presence || span == 0) return TML_ERR_ARG;
+  if (!c->win_ready) return set_err(TML_ERR_STATE, "tml_win_presence before tml_win_prepare");
+  if (span >> 32) return set_err(TML_ERR_UNSUPPORTED, "step-id span %llu too wide", (u64)span);
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure(&c->d_rowof[kind], &c->cap_span[kind], span);
+  if (rc != TML_OK) return rc;
+  // a rank without candidates must not constrain the intersection: all ones
+  if (c->win_n == 0 || c->win_ncand[kind] == 0) { CK(cudaMemsetAsync(presence, 1, span, s)); return TML_OK; }
+  CK(cudaMemsetAsync(presence, 0, span, s));
+  const u32 want = kind == TML_KIND_TIME ? RF_CAND_T : RF_CAND_M;
+  const int grid = grid_for(c, c->win_n, 256);
+  k_presence<<<grid, 256, 0, s>>>(c->d_steps, c->d_flags, c->win_n, want, glo, span, presence,
+                                  c->d_rowof[kind]);
+  CK(cudaPeekAtLastError());
+  return TML_OK;
+}
+
+int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const uint8_t* presence,
+                   uint32_t window, void* stream, tml_align_info* out) {
+  if (!c || kind > 1 || !out || window == 0) return TML_ERR_ARG;
+  if (!c->win_ready) return set_err(TML_ERR_STATE, "tml_win_select before tml_win_prepare");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  c->n_common[kind] = 0;
+  if (span == 0 || !presence) return TML_OK;
+  const u32 nb = (u32)((span + SEL_TILE - 1) / SEL_TILE);
+  int rc = ensure(&c->d_blockcnt, &c->cap_blk, nb);
+  if (rc != TML_OK) return rc;
+  const u64 maxsel = span < window ? span : window;
+  if (maxsel > c->cap_sel) {
+    cudaFree(c->d_selrow); cudaFree(c->d_selstep);
+    c->d_selrow = nullptr; c->d_selstep = nullptr; c->cap_sel = 0;
+    CK(cudaMalloc(&c->d_selrow, (size_t)maxsel * sizeof(u32)));
+    CK(cudaMalloc(&c->d_selstep, (size_t)maxsel * sizeof(u64)));
+    c->cap_sel = maxsel;
+  }
+  rc = ensure(&c->d_xrows[kind], &c->cap_x[kind], maxsel, true);
+  if (rc != TML_OK) return rc;
+  k_sel_count<<<nb, SEL_THREADS, 0, s>>>(presence, span, c->d_blockcnt);
+  CK(cudaPeekAtLastError());
+  k_sel_scan<<<1, 1024, 0, s>>>(c->d_blockcnt, nb, c->d_total);
+  CK(cudaPeekAtLastError());
+  k_sel_scatter<<<nb, SEL_THREADS, 0, s>>>(presence, span, c->d_blockcnt, c->d_total, (u64)window,
+                                           glo, c->d_rowof[kind], c->d_selrow, c->d_selstep);
+  CK(cudaPeekAtLastError());
+  char* st = (char*)c->h_stage;
+  CK(cudaMemcpyAsync(st, c->d_total, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  u64 total = 0;
+  memcpy(&total, st, sizeof(u64));
+  const u64 keep = total < window ? total : window;
+  c->n_common[kind] = keep;
+  out->n_common = keep;
+  if (keep == 0) return TML_OK;
+  // a rank that has no candidates of its own does not own rows for the window
+  if (c->win_n == 0 || c->win_ncand[kind] == 0) return TML_OK;
+  const int grid = grid_for(c, keep * 4, GA_THREADS);
+  k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, c->d_selrow, keep, c->d_xrows[kind], c->d_partials);
+  CK(cudaPeekAtLastError());
+  k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
+  CK(cudaPeekAtLastError());
+  CK(cudaMemcpyAsync(st + 64, c->d_final, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 256, c->d_selstep, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 264, c->d_selstep + (keep - 1), sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double f[16];
+  memcpy(f, st + 64, sizeof(f));
+  // partial layout [q][k]: q0 {dl} q1 {fwd,bwd} q2 {opt,cpu,traced,total} q3 {alloc,resv,maxa,maxr}
+  out->t_sums[0] = f[0]; out->t_sums[1] = f[4]; out->t_sums[2] = f[5]; out->t_sums[3] = f[8];
+  out->t_sums[4] = f[9]; out->t_sums[5] = f[10]; out->t_sums[6] = f[11];
+  out->m_sums[0] = f[12]; out->m_sums[1] = f[13]; out->m_sums[2] = f[14]; out->m_sums[3] = f[15];
+  memcpy(&out->start_step, st + 256, sizeof(u64));
+  memcpy(&out->end_step, st + 264, sizeof(u64));
+  out->n_rows = keep;
+  return TML_OK;
+}
+
+const void* tml_win_rows(tml_ctx* c, uint32_t kind) {
+  if (!c || kind > 1) return nullptr;
+  return c->d_xrows[kind];
+}
+
+int tml_win_rows_export(tml_ctx* c, uint32_t kind, void* handle64) {
+  if (!c || kind > 1 || !handle64) return TML_ERR_ARG;
+  if (!c->d_xrows[kind]) return set_err(TML_ERR_STATE, "no aligned rows to export");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle is 64 B");
+  CK(cudaSetDevice(c->device));
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, c->d_xrows[kind]));
+  return TML_OK;
+}
+
+int tml_peer_open(tml_ctx* c, const void* handle64, void** peer_ptr) {
+  if (!c || !handle64 || !peer_ptr) return TML_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  std::string key((const char*)handle64, 64);
+  auto it = c->peers.find(key);
+  if (it != c->peers.end()) { *peer_ptr = it->second; return TML_OK; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peers.emplace(key, p);
+  *peer_ptr = p;
+  return TML_OK;
+}
+
+int tml_peer_close(tml_ctx* c, void* peer_ptr) {
+  if (!c || !peer_ptr) return TML_ERR_ARG;
+  for (auto it = c->peers.begin(); it != c->peers.end(); ++it) {
+    if (it->second == peer_ptr) {
+      CK(cudaIpcCloseMemHandle(peer_ptr));
+      c->peers.erase(it);
+      return TML_OK;
+    }
+  }
+  return TML_ERR_ARG;
+}
+
+}  // extern "C"
+
+template <int R>
+static void launch_reduce(int grid, cudaStream_t s, const ReduceParams& p) {
+  k_window_reduce<R><<<grid, RD_THREADS, 0, s>>>(p);
+}
+
+extern "C" {
+
+int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
+  if (!c || !a || !a->series || a->n_ranks == 0 || a->n_ranks > TML_MAX_RANKS) return TML_ERR_ARG;
+  if (a->shard_hi > a->n_common || a->shard_lo > a->shard_hi) return TML_ERR_ARG;
+  if (a->shard_hi == a->shard_lo) return TML_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  ReduceParams p;
+  memset(&p, 0, sizeof(p));
+  for (u32 r = 0; r < a->n_ranks; ++r) {
+    if (!a->rows[r]) return set_err(TML_ERR_ARG, "rows[%u] is NULL", r);
+    p.rows[r] = (const uint4*)a->rows[r];
+  }
+  p.series = a->series; p.n_common = a->n_common;
+  p.shard_lo = a->shard_lo; p.shard_hi = a->shard_hi;
+  p.mask = a->mask; p.n_ranks = a->n_ranks;
+  const int grid = grid_for(c, (a->shard_hi - a->shard_lo) * 4, RD_THREADS);
+  switch (a->n_ranks) {
+    case 1: launch_reduce<1>(grid, s, p); break;
+    case 2: launch_reduce<2>(grid, s, p); break;
+    case 3: launch_reduce<3>(grid, s, p); break;
+    case 4: launch_reduce<4>(grid, s, p); break;
+    case 5: launch_reduce<5>(grid, s, p); break;
+    case 6: launch_reduce<6>(grid, s, p); break;
+    case 7: launch_reduce<7>(grid, s, p); break;
+    case 8: launch_reduce<8>(grid, s, p); break;
+    default: k_window_reduce_any<<<grid, RD_THREADS, 0, s>>>(p); break;
+  }
+  CK(cudaPeekAtLastError());
+  return TML_OK;
+}
+
+int tml_win_bands(tml_ctx* c, const double* series, const tml_band_args* a, void* stream,
+                  tml_band_out* out) {
+  if (!c || !series || !a || !out) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  BandParams p;
+  p.series = series; p.n_common = a->n_common; p.shard_lo = a->shard_lo; p.shard_hi = a->shard_hi;
+  memcpy(p.lo, a->band_lo, sizeof(p.lo));
+  memcpy(p.hi, a->band_hi, sizeof(p.hi));
+  memcpy(p.tail_first, a->tail_first, sizeof(p.tail_first));
+  double* d_sum = c->d_final;            // 48 doubles
+  double* d_tail = c->d_partials;        // 32 doubles (scratch)
+  k_bands<<<dim3(16, 4), 256, 0, s>>>(p, d_sum, c->d_bandcnt, d_tail);
+  CK(cudaPeekAtLastError());
+  char* st = (char*)c->h_stage;
+  CK(cudaMemcpyAsync(st, d_sum, 48 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 512, c->d_bandcnt, 48 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 1024, d_tail, 32 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  memcpy(out->sum, st, 48 * sizeof(double));
+  memcpy(out->cnt, st + 512, 48 * sizeof(u64));
+  double tails[32];
+  memcpy(tails, st + 1024, sizeof(tails));
+  for (int k = 0; k < 16; ++k) { out->tail_first[k] = tails[2 * k]; out->tail_last[k] = tails[2 * k + 1]; }
+  return TML_OK;
+}
+
+int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* out) {
+  if (!c || !out || max_rows == 0) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  out->max_ratio = -1.0;
+  const u64 total = c->proc_commits.load();
+  u64 n = total < c->proc_slots ? total : c->proc_slots;
+  if (n > max_rows) n = max_rows;
+  if (n == 0) return TML_OK;
+  const u64 first_k = total - n;
+  const int grid = grid_for(c, n, PR_THREADS);
+  k_proc_reduce<<<grid, PR_THREADS, 0, s>>>(c->d_pring, c->proc_slots, first_k, n, c->d_partials);
+  CK(cudaPeekAtLastError());
+  k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, PR_COLS, PR_MAXMASK, c->d_final);
+  CK(cudaPeekAtLastError());
+  char* st = (char*)c->h_stage;
+  CK(cudaMemcpyAsync(st, c->d_final, PR_COLS * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double f[PR_COLS];
+  memcpy(f, st, sizeof(f));
+  out->n = n;
+  out->n_gpu = (u64)f[14];
+  out->sum_cpu = f[0]; out->max_cpu = f[4];
+  out->sum_rss = f[1]; out->max_rss = f[5];
+  out->sum_used = f[2]; out->max_used = out->n_gpu ? f[6] : 0.0;
+  out->sum_resv = f[3]; out->max_resv = out->n_gpu ? f[7] : 0.0;
+  out->max_total = out->n_gpu ? f[8] : 0.0;
+  out->max_ratio = (f[9] > -INFINITY) ? f[9] : -1.0;
+  out->ts_max = f[10]; out->ts_min = -f[11];
+  out->max_cores = (u32)f[12];
+  out->any_gpu_available = f[13] > 0.5 ? 1u : 0u;
+  return TML_OK;
+}
+
+}  // extern "C"

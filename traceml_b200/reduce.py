@@ -1,0 +1,399 @@
+"""Cross-rank window reduce: the B200-native final-summary path.
+
+Replaces, for the Step-Time / Step-Memory / Process sections, the reference's
+TCP -> SQLite -> single-core Python chain
+(``src/traceml/reporting/sections/*/loader.py`` + ``diagnostics/*``): every
+rank's window stays resident in its own HBM ring; ranks agree on the common
+step window with two tiny collectives, exchange their aligned 64-B rows once
+over NVLink (peer loads fused into the reduce kernel, or one NCCL all-gather),
+and each GPU reduces its shard of the steps.
+
+Host side only sequences kernels and collectives; all per-step arithmetic is
+in ``csrc/tml_engine.cu``, all rank-level rules in ``csrc/tml_diag.cpp``.
+
+One process may drive several engines ("local ranks") -- production uses one,
+single-GPU tests use several to play a whole job on one device.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+
+from . import _abi
+
+KIND_TIME, KIND_MEM = _abi.KIND_TIME, _abi.KIND_MEM
+
+# analytics/trends/schema.py:27-62
+_BANDS = ((0.15, 0.25), (0.45, 0.55), (0.90, 1.00))
+_HISTORY_LIMIT = 10_000
+
+
+# ----------------------------------------------------------------------------- comm
+class LocalComm:
+    """Single process: every collective is the identity."""
+
+    world = 1
+    index = 0
+
+    def all_gather_obj(self, obj: Any) -> List[Any]:
+        return [obj]
+
+    def all_reduce_min_(self, t: torch.Tensor) -> None:
+        return None
+
+    def all_gather_into(self, out: torch.Tensor, inp: torch.Tensor) -> None:
+        out.copy_(inp)
+
+    def barrier(self) -> None:
+        return None
+
+
+class TorchDistComm:
+    """torch.distributed plumbing (NCCL over NVLink on the box, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.index = dist.get_rank(group)
+
+    def all_gather_obj(self, obj: Any) -> List[Any]:
+        out: List[Any] = [None] * self.world
+        self._dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def all_reduce_min_(self, t: torch.Tensor) -> None:
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
+
+    def all_gather_into(self, out: torch.Tensor, inp: torch.Tensor) -> None:
+        self._dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def barrier(self) -> None:
+        self._dist.barrier(group=self.group)
+
+
+# ----------------------------------------------------------------------------- helpers
+def _band_bounds(n: int, band) -> tuple:
+    """analytics/trends/core.py:38-49."""
+    start = int(math.floor(n * float(band[0])))
+    end = int(math.ceil(n * float(band[1])))
+    start = max(0, min(start, n - 1))
+    end = max(start + 1, min(end, n))
+    return start, end
+
+
+def trend_layout(n: int, *, min_points: int, warmup_frac: float):
+    """Global series index ranges of the three trend bands, or None if the
+    series is too short (analytics/trends/core.py:51-84)."""
+    if n < min_points:
+        return None
+    length = min(n, _HISTORY_LIMIT)
+    if length < min_points:
+        return None
+    off = n - length
+    warm = int(math.floor(length * float(warmup_frac)))
+    stable = length - warm
+    if stable < min_points:
+        return None
+    out = []
+    for b in _BANDS:
+        s, e = _band_bounds(stable, b)
+        out.append((off + warm + s, off + warm + e))
+    return out
+
+
+def _stream_of(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream) if device.type == "cuda" else 0
+
+
+@dataclass
+class RankWindow:
+    """What one global rank contributed to one aligned window."""
+
+    rank: int
+    n_rows: int = 0
+    t_sums: Sequence[float] = ()
+    m_sums: Sequence[float] = ()
+    info: Dict[str, Any] = field(default_factory=dict)
+
+
+@dataclass
+class KindResult:
+    observed: int = 0            # ranks that had candidates
+    used: List[int] = field(default_factory=list)
+    n_common: int = 0
+    start_step: Optional[int] = None
+    end_step: Optional[int] = None
+    windows: Dict[int, RankWindow] = field(default_factory=dict)
+    band_sum: Optional[List[List[float]]] = None   # [16][3]
+    band_cnt: Optional[List[List[int]]] = None
+    tail_first: Optional[List[float]] = None
+    tail_last: Optional[List[float]] = None
+    series: Optional[torch.Tensor] = None          # this process's [16, n_common] (own shard valid)
+    shard: tuple = (0, 0)
+
+
+@dataclass
+class ReduceOutput:
+    window: int
+    ranks: List[int]
+    infos: Dict[int, Dict[str, Any]]
+    time: KindResult
+    mem: KindResult
+    exchange: str
+    fused_pass: bool
+    timings_ms: Dict[str, float] = field(default_factory=dict)
+
+
+# ----------------------------------------------------------------------------- reducer
+class WindowReducer:
+    """Sequences the reduce stages for the local engines of this process."""
+
+    def __init__(self, engines: Sequence[Any], comm: Any = None, *, device: Optional[torch.device] = None,
+                 exchange: str = "auto"):
+        self.engines = list(engines)
+        self.comm = comm or LocalComm()
+        self.device = device or torch.device("cuda", self.engines[0].device)
+        self.L = len(self.engines)
+        self.exchange = exchange
+        self._series_cache: Dict[int, torch.Tensor] = {}
+
+    # global rank of local engine l
+    def _grank(self, l: int) -> int:
+        return self.comm.index * self.L + l
+
+    def _info_dict(self, w) -> Dict[str, Any]:
+        return {
+            "n_retained": int(w.n_retained), "latest_step": int(w.latest_step),
+            "monotone": int(w.monotone), "dup_rows": int(w.dup_rows),
+            "n_rows": [int(w.n_rows[0]), int(w.n_rows[1])],
+            "n_cand": [int(w.n_cand[0]), int(w.n_cand[1])],
+            "lo": [int(w.lo[0]), int(w.lo[1])], "hi": [int(w.hi[0]), int(w.hi[1])],
+            "t_sums": [float(x) for x in w.t_sums], "t_count": int(w.t_count),
+        }
+
+    def reduce(self, window: int, *, want_series: bool = False) -> ReduceOutput:
+        window = max(1, int(window))
+        dev = self.device
+        stream = _stream_of(dev)
+        R = self.comm.world * self.L
+        ev = None
+        timings: Dict[str, float] = {}
+        if dev.type == "cuda":
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record()
+
+        # ---- stage 1: local windows + bounds
+        local_infos = [self._info_dict(e.win_prepare(window, stream)) for e in self.engines]
+        gathered = self.comm.all_gather_obj(local_infos)
+        infos: Dict[int, Dict[str, Any]] = {}
+        for p, lst in enumerate(gathered):
+            for l, d in enumerate(lst):
+                infos[p * self.L + l] = d
+        ranks = sorted(infos)
+        if ev:
+            ev[1].record()
+
+        results = []
+        for kind in (KIND_TIME, KIND_MEM):
+            results.append(self._align(kind, window, infos, ranks, stream))
+        t_res, m_res = results
+        if ev:
+            ev[2].record()
+
+        # ---- stage 4: exchange + per-step reduce
+        same = (t_res.n_common > 0 and t_res.n_common == m_res.n_common
+                and t_res.start_step == m_res.start_step and t_res.end_step == m_res.end_step
+                and t_res.used == m_res.used)
+        mode = self._exchange_mode()
+        if same:
+            self._reduce_pass(KIND_TIME, _abi.MASK_TIME | _abi.MASK_MEM, t_res, stream, mode)
+            m_res.series, m_res.shard = t_res.series, t_res.shard
+        else:
+            if t_res.n_common:
+                self._reduce_pass(KIND_TIME, _abi.MASK_TIME, t_res, stream, mode)
+            if m_res.n_common:
+                self._reduce_pass(KIND_MEM, _abi.MASK_MEM, m_res, stream, mode)
+        if ev:
+            ev[3].record()
+
+        # ---- stage 5: trend bands
+        self._bands(t_res, m_res, same, stream)
+        if ev:
+            ev[4].record()
+            torch.cuda.synchronize(dev)
+            names = ["prepare", "align", "reduce", "bands"]
+            for i, nm in enumerate(names):
+                timings[nm] = float(ev[i].elapsed_time(ev[i + 1]))
+            timings["total"] = float(ev[0].elapsed_time(ev[4]))
+        if not want_series:
+            pass
+        return ReduceOutput(window=window, ranks=ranks, infos=infos, time=t_res, mem=m_res,
+                            exchange=mode, fused_pass=same, timings_ms=timings)
+
+    # ------------------------------------------------------------------ alignment
+    def _align(self, kind: int, window: int, infos, ranks, stream) -> KindResult:
+        res = KindResult()
+        part = [r for r in ranks if infos[r]["n_cand"][kind] > 0]
+        res.observed = len(part)
+        if not part:
+            return res
+        glo = max(infos[r]["lo"][kind] for r in part)
+        ghi = min(infos[r]["hi"][kind] for r in part)
+        if ghi < glo:
+            return res
+        span = ghi - glo + 1
+        dev = self.device
+        presence = None
+        for l, e in enumerate(self.engines):
+            p = torch.empty(span, dtype=torch.uint8, device=dev)
+            e.win_presence(kind, glo, span, p, stream)
+            presence = p if presence is None else torch.minimum(presence, p)
+        self.comm.all_reduce_min_(presence)
+        aligns = []
+        for l, e in enumerate(self.engines):
+            a = e.win_select(kind, glo, span, presence, window, stream)
+            aligns.append({
+                "n_common": int(a.n_common), "start": int(a.start_step), "end": int(a.end_step),
+                "n_rows": int(a.n_rows), "t_sums": [float(x) for x in a.t_sums],
+                "m_sums": [float(x) for x in a.m_sums],
+            })
+        gathered = self.comm.all_gather_obj(aligns)
+        n_common = max(a["n_common"] for lst in gathered for a in lst)
+        res.n_common = n_common
+        if n_common == 0:
+            return res
+        for p, lst in enumerate(gathered):
+            for l, a in enumerate(lst):
+                r = p * self.L + l
+                if r in part and a["n_rows"] > 0:
+                    res.windows[r] = RankWindow(rank=r, n_rows=a["n_rows"], t_sums=a["t_sums"],
+                                                m_sums=a["m_sums"], info=infos[r])
+                    res.start_step, res.end_step = a["start"], a["end"]
+        res.used = sorted(res.windows)
+        return res
+
+    # ------------------------------------------------------------------ exchange
+    def _exchange_mode(self) -> str:
+        if self.comm.world == 1:
+            return "local"
+        if self.exchange in ("p2p", "nccl"):
+            return self.exchange
+        return "p2p" if self.device.type == "cuda" else "nccl"
+
+    def _reduce_pass(self, kind: int, mask: int, res: KindResult, stream, mode: str) -> None:
+        n = res.n_common
+        used = res.used
+        R = len(used)
+        dev = self.device
+        # series buffer of this process: [16, n]; only this process's shard is written
+        series = torch.empty(_abi.TML_SERIES_PER_STEP * n, dtype=torch.float64, device=dev)
+        my = [self._grank(l) for l in range(self.L)]
+        # rows handle per used rank
+        rows: Dict[int, Any] = {}
+        local_used = [r for r in used if r in my]
+        if mode == "local":
+            for r in used:
+                rows[r] = self.engines[r - self.comm.index * self.L].win_rows_tensor(kind, n)
+        elif mode == "nccl":
+            # one all-gather of the dense aligned rows; ranks outside `used` send zeros
+            W = self.comm.world * self.L
+            gathered = torch.empty(W * n * 8, dtype=torch.float64, device=dev)
+            local = torch.zeros(self.L * n * 8, dtype=torch.float64, device=dev)
+            for l in range(self.L):
+                if self._grank(l) in used:
+                    local[l * n * 8:(l + 1) * n * 8].copy_(self.engines[l].win_rows_tensor(kind, n))
+            self.comm.all_gather_into(gathered, local)
+            for r in used:
+                rows[r] = gathered[r * n * 8:(r + 1) * n * 8]
+            self._keep = gathered
+        else:  # p2p: CUDA-IPC peer mappings, loads fused into the reduce kernel
+            handles = {}
+            for l in range(self.L):
+                if self._grank(l) in used:
+                    handles[self._grank(l)] = self.engines[l].win_rows_export(kind)
+            allh = {}
+            for d in self.comm.all_gather_obj(handles):
+                allh.update(d)
+            e0 = self.engines[0]
+            for r in used:
+                if r in my:
+                    rows[r] = self.engines[r - self.comm.index * self.L].win_rows_tensor(kind, n)
+                else:
+                    rows[r] = e0.peer_open(allh[r])
+            self.comm.barrier()  # every rank's rows are complete before peers read them
+        # step-sharded: shard s of W_total shards -> engine with global rank s
+        W = self.comm.world * self.L
+        lo_first, hi_last = None, None
+        for l, e in enumerate(self.engines):
+            g = self._grank(l)
+            lo = (n * g) // W
+            hi = (n * (g + 1)) // W
+            if lo_first is None:
+                lo_first = lo
+            hi_last = hi
+            if hi > lo:
+                e.win_reduce([rows[r] for r in used], mask, n, lo, hi, series, stream)
+        res.series = series.view(_abi.TML_SERIES_PER_STEP, n)
+        res.shard = (lo_first or 0, hi_last or 0)
+        if mode == "p2p":
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+            self.comm.barrier()  # nobody frees / rewrites rows while a peer still reads
+
+    # ------------------------------------------------------------------ bands
+    def _bands(self, t_res: KindResult, m_res: KindResult, same: bool, stream) -> None:
+        def run(res: KindResult, kinds):
+            n = res.n_common
+            if n == 0 or res.series is None:
+                return
+            a = _abi.BandArgs()
+            a.n_common = n
+            a.shard_lo, a.shard_hi = res.shard
+            lay_t = trend_layout(n, min_points=200, warmup_frac=0.10)
+            lay_m = trend_layout(n, min_points=50, warmup_frac=0.0)
+            for k, lay in ((0, lay_t), (1, lay_m)):
+                for b in range(3):
+                    a.band_lo[k][b] = lay[b][0] if lay else 0
+                    a.band_hi[k][b] = lay[b][1] if lay else 0
+            a.tail_first[0] = 0
+            a.tail_first[1] = n - min(n, 1000)
+            out = self.engines[0].win_bands(res.series, a, stream)
+            part = {
+                "sum": [[float(out.sum[s][b]) for b in range(3)] for s in range(16)],
+                "cnt": [[int(out.cnt[s][b]) for b in range(3)] for s in range(16)],
+                "tf": [float(out.tail_first[s]) for s in range(16)],
+                "tl": [float(out.tail_last[s]) for s in range(16)],
+            }
+            parts = self.comm.all_gather_obj(part)
+            res.band_sum = [[sum(p["sum"][s][b] for p in parts) for b in range(3)] for s in range(16)]
+            res.band_cnt = [[sum(p["cnt"][s][b] for p in parts) for b in range(3)] for s in range(16)]
+
+            def pick(key, s):
+                for p in parts:
+                    v = p[key][s]
+                    if not math.isnan(v):
+                        return v
+                return float("nan")
+
+            res.tail_first = [pick("tf", s) for s in range(16)]
+            res.tail_last = [pick("tl", s) for s in range(16)]
+            res._lay = (lay_t, lay_m)
+
+        run(t_res, (0,))
+        if same:
+            m_res.band_sum, m_res.band_cnt = t_res.band_sum, t_res.band_cnt
+            m_res.tail_first, m_res.tail_last = t_res.tail_first, t_res.tail_last
+            m_res._lay = getattr(t_res, "_lay", (None, None))
+        else:
+            run(m_res, (1,))
+
+
+__all__ = ["WindowReducer", "LocalComm", "TorchDistComm", "ReduceOutput", "KindResult",
+           "RankWindow", "trend_layout"]
