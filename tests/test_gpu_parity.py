@@ -1,0 +1,180 @@
+"""GPU parity tests proper: the CUDA path, through the C-ABI, against
+ (a) the committed golden vectors (the reference's own outputs) and
+ (b) the oracle on the same seeded inputs.
+
+Every case plays all R ranks on one GPU (one engine per rank); the cross-rank
+kernels see exactly what they would see after an NVLink exchange.
+Tolerances: step ids / rank ids / labels / issue order exact,
+floats rel <= 1e-9 (summation order only)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (REL_TOL, assert_struct, golden_cases, oracle_mem_rows, oracle_proc_rows,
+                     oracle_time_rows, plain, proc_replay_for, step_replay_for, strip_device)
+
+pytestmark = pytest.mark.gpu
+
+STEP = golden_cases("step")
+PROC = golden_cases("process")
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def _summary(records, window, procs=None, ring_slots=None, ranks=None):
+    from traceml_b200 import replay, sections
+    from traceml_b200.engine import Engine
+
+    R = len(records) if records is not None else len(procs)
+    engines = []
+    for r in range(R):
+        n = len(records[r]) if records is not None else 0
+        e = Engine(device=0, rank=r, world=R, ring_slots=ring_slots or max(64, n + 8),
+                   proc_slots=max(64, (len(procs[r]) if procs else 0) + 8))
+        if records is not None and n:
+            e.load_steps(records[r])
+        if procs is not None:
+            e.load_procs(procs[r])
+        engines.append(e)
+    torch.cuda.synchronize()
+    try:
+        return sections.SummaryEngine(engines, ram_total=replay.PROC_RAM_TOTAL_BYTES,
+                                      gpu_count=R).build(window, window)
+    finally:
+        for e in engines:
+            e.close()
+
+
+@pytest.mark.parametrize("g", STEP, ids=[g["case"] for g in STEP])
+def test_step_time_vs_golden(cuda, g):
+    recs = step_replay_for(g)
+    got = _summary(recs, g["window"])["step_time"]
+    ref = g["step_time"]
+    assert_struct(plain(got["data"]), ref["data"], "data")
+    assert_struct(plain(got["diagnosis"]), ref["diagnosis"], "diagnosis")
+    for k in ("average", "median", "worst"):
+        assert_struct(plain(got["global"][k]), ref["payload"]["global"][k], f"global.{k}")
+
+
+@pytest.mark.parametrize("g", STEP, ids=[g["case"] for g in STEP])
+def test_step_memory_vs_golden(cuda, g):
+    recs = step_replay_for(g)
+    got = _summary(recs, g["window"])["step_memory"]
+    ref = g["step_memory"]
+    assert got["training_steps"] == ref["training_steps"]
+    assert got["latest_step_observed"] == ref["latest_step_observed"]
+    assert_struct(plain(got["window"]), ref["window"], "window")
+    assert_struct(plain(got["metrics"]), ref["metrics"], "metrics")
+    assert_struct(plain(got["per_global_rank"]), ref["per_global_rank"], "rows")
+    gd, rd = strip_device(plain(got["diagnosis"])), strip_device(ref["diagnosis"])
+    assert_struct(gd["primary"], rd["primary"], "primary")
+    assert_struct(gd["issues"], rd["issues"], "issues")
+    for k, sig in rd["metric_attribution"].items():
+        assert_struct({x: gd["metric_attribution"][k][x] for x in sig}, sig, f"attr.{k}")
+    if ref["payload"].get("global") and ref["window"]["n_steps"]:
+        for k in ("average", "median", "worst"):
+            assert_struct(plain(got["global"][k]), ref["payload"]["global"][k], f"global.{k}")
+
+
+@pytest.mark.parametrize("g", [g for g in STEP if "step_memory_with_total" in g],
+                         ids=[g["case"] for g in STEP if "step_memory_with_total" in g])
+def test_step_memory_pressure_vs_golden(cuda, g):
+    from traceml_b200 import replay
+
+    recs = step_replay_for(g)
+    procs = replay.make_proc_replay("normal", g["ranks"], 50, g["seed"])
+    got = _summary(recs, g["window"], procs=procs)["step_memory"]
+    t = g["step_memory_with_total"]
+    assert got["gpu_total_bytes"] == t["gpu_total_bytes"]
+    gd, rd = strip_device(plain(got["diagnosis"])), strip_device(t["diagnosis"])
+    assert_struct(gd["primary"], rd["primary"], "primary")
+    assert_struct(gd["issues"], rd["issues"], "issues")
+
+
+@pytest.mark.parametrize("g", PROC, ids=[g["case"] for g in PROC])
+def test_process_vs_golden(cuda, g):
+    procs = proc_replay_for(g)
+    got = plain(_summary(None, g["max_rows"], procs=procs)["process"])
+    ref = g["process"]
+    assert_struct(got["primary"], ref["diagnosis"]["primary"], "primary")
+    assert_struct(got["issues"], ref["diagnosis"]["issues"], "issues")
+    ragg = dict(ref["aggregate"])
+    ragg.pop("gpu_mem_reserved_overhang_ratio", None)
+    assert_struct(got["aggregate"], ragg, "aggregate")
+    for r, pr in ref["per_global_rank"].items():
+        mine = got["per_global_rank"][r]
+        assert_struct(mine, {k: pr[k] for k in mine}, f"rank{r}")
+
+
+def test_series_vs_oracle(cuda):
+    """Per-step cross-rank median / worst series, element by element."""
+    from oracle import step_memory_oracle, step_time_oracle
+    from traceml_b200 import replay
+
+    R, S, W = 5, 777, 512
+    recs = replay.make_step_replay("ragged", R, S, seed=42)
+    out = _summary(recs, W)["reduce"]
+    o = step_time_oracle.step_time_section(oracle_time_rows(recs, W), max_rows=W)
+    steps = step_time_oracle.common_suffix_steps(o["data"]["aligned_step_metrics"], W)
+    assert out.time.n_common == len(steps)
+    ser = out.time.series.cpu().numpy()
+    for mi, key in enumerate(step_time_oracle.METRIC_KEYS):
+        ref = step_time_oracle.metric_series(key, steps, o["data"]["aligned_step_metrics"])
+        np.testing.assert_allclose(ser[2 * mi], ref["median"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(ser[2 * mi + 1], ref["worst"], rtol=1e-12, atol=0)
+    win = step_memory_oracle.aligned_window(oracle_mem_rows(recs), W)
+    mets = step_memory_oracle.combined_metrics(win)
+    mser = out.mem.series.cpu().numpy()
+    for mi, m in enumerate(mets):
+        np.testing.assert_array_equal(mser[12 + 2 * mi], np.asarray(m["series"]["median"]))
+        np.testing.assert_array_equal(mser[13 + 2 * mi], np.asarray(m["series"]["worst"]))
+
+
+def test_ring_wrap_and_window(cuda):
+    """Ring smaller than the history: only the retained rows count
+    (the reference prunes to 1.5 x window rows, sqlite_writer.py:394-424)."""
+    from oracle import step_time_oracle
+    from traceml_b200 import replay
+
+    R, S, slots, W = 3, 1000, 300, 200
+    recs = replay.make_step_replay("balanced", R, S, seed=5)
+    got = _summary(recs, W, ring_slots=slots)["step_time"]
+    kept = {r: recs[r][-slots:] for r in recs}
+    ref = step_time_oracle.step_time_section(oracle_time_rows(kept, W), max_rows=W)
+    assert_struct(plain(got["data"]["aligned_summary"]), plain(ref["data"]["aligned_summary"]), "aligned")
+    assert_struct(plain(got["data"]["aligned_window"]), plain(ref["data"]["aligned_window"]), "window")
+    assert_struct(plain(got["diagnosis"]), plain(ref["diagnosis"]), "diagnosis")
+
+
+def test_large_window_properties(cuda):
+    """BASELINE-size window (W = 10^6, R = 8): size-independent properties --
+    identical ranks => median == worst == the rank's own series; permuting the
+    ranks leaves every series bit-identical."""
+    from traceml_b200 import _abi, replay, sections
+    from traceml_b200.engine import Engine
+    from traceml_b200.reduce import WindowReducer
+
+    R, S = 8, 1_000_000
+    base = replay.make_step_replay("balanced", 1, S, seed=9)[0]
+    engines = [Engine(device=0, rank=r, world=R, ring_slots=S) for r in range(R)]
+    for e in engines:
+        e.load_steps(base)
+    torch.cuda.synchronize()
+    out = WindowReducer(engines).reduce(S)
+    assert out.time.n_common == S and out.fused_pass
+    ser = out.time.series
+    assert torch.equal(ser[8], ser[9])       # step_time median == worst
+    assert torch.equal(ser[12], ser[13])     # peak_allocated median == worst
+    wall = torch.from_numpy((base["dur_ns"][:, 5].astype(np.float64) / 1.0e6)).cuda()
+    comp = torch.from_numpy(((base["dur_ns"][:, 2].astype(np.float64) / 1e6
+                              + base["dur_ns"][:, 3].astype(np.float64) / 1e6)
+                             + base["dur_ns"][:, 4].astype(np.float64) / 1e6)).cuda()
+    assert torch.equal(ser[8], torch.maximum(wall, comp))
+    for e in engines:
+        e.close()

@@ -1,0 +1,165 @@
+"""GPU: the per-step path -- stamp / commit kernels behind timed_region / trace_step."""
+import time
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def _spin(ms: float):
+    torch.cuda._sleep(int(ms * 1.0e6 * 1.4))  # ~cycles; only needs to be "a while"
+
+
+def test_stamp_matches_cuda_events(cuda):
+    """K1 durations vs cudaEvent.elapsed_time around the same work
+    (|d| <= 2 us + 1 % per phase)."""
+    from traceml_b200.engine import Engine
+
+    eng = Engine(device=0, ring_slots=256)
+    s = torch.cuda.current_stream()
+    a = torch.randn(2048, 2048, device="cuda")
+    evs = []
+    for step in range(1, 33):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        slot = eng.phase_begin(2, s.cuda_stream)
+        assert slot >= 0
+        for _ in range(1 + step % 4):
+            a = a @ a
+            a = a / a.norm()
+        assert eng.phase_end(2, slot, s.cuda_stream) == 0
+        e1.record()
+        evs.append((e0, e1))
+        assert eng.step_commit(step, 1000 + step, 2000 + step, 1, time.time(), s.cuda_stream) == 0
+    torch.cuda.synchronize()
+    recs, dropped = eng.drain()
+    assert dropped == 0 and len(recs) == 32
+    assert list(recs["step"]) == list(range(1, 33))
+    assert list(recs["peak_alloc"]) == [1000 + i for i in range(1, 33)]
+    assert (recs["n_calls"][:, 2] == 1).all() and (recs["gpu_mask"] == 4).all()
+    for (e0, e1), r in zip(evs, recs):
+        ev_us = e0.elapsed_time(e1) * 1000.0
+        k_us = float(r["dur_ns"][2]) / 1000.0
+        # the event pair brackets the stamp pair, so it can only be (slightly) longer
+        assert k_us <= ev_us + 2.0
+        assert abs(ev_us - k_us) <= 2.0 + 0.01 * ev_us + 12.0, (ev_us, k_us)
+    eng.close()
+
+
+def test_accumulate_and_host_phases(cuda):
+    """Repeated regions sum and count n_calls (a7); host-clock phases merge at commit."""
+    from traceml_b200.engine import Engine
+
+    eng = Engine(device=0, ring_slots=64)
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.zeros(1 << 20, device="cuda")
+    for _ in range(3):
+        slot = eng.phase_begin(1, s)
+        x += 1
+        eng.phase_end(1, slot, s)
+    eng.phase_host(0, 1_234_567)
+    eng.phase_host(0, 1_000_000)
+    eng.phase_host(5, 40_000_000)
+    assert eng.step_commit(7, 0, 0, 0, 123.5, s) == 0
+    # next step starts clean
+    eng.phase_host(5, 1_000)
+    assert eng.step_commit(8, 0, 0, 0, 124.5, s) == 0
+    torch.cuda.synchronize()
+    recs, _ = eng.drain()
+    assert len(recs) == 2
+    r = recs[0]
+    assert int(r["n_calls"][1]) == 3 and int(r["dur_ns"][1]) > 0
+    assert int(r["dur_ns"][0]) == 2_234_567 and int(r["n_calls"][0]) == 2
+    assert int(r["dur_ns"][5]) == 40_000_000 and float(r["host_ts"]) == 123.5
+    assert int(r["gpu_mask"]) == 2 and int(r["flags"]) == 0
+    r2 = recs[1]
+    assert int(r2["dur_ns"][1]) == 0 and int(r2["n_calls"][1]) == 0 and int(r2["dur_ns"][5]) == 1_000
+    live = eng.live()
+    assert live.steps_committed == 2 and live.phase[5].count == 2
+    assert live.phase[5].worst_ns == 40_000_000
+    eng.close()
+
+
+def test_live_running_median(cuda):
+    """Warp-shuffle running median from the log histogram: within one sub-bin (6.25 %)."""
+    from traceml_b200.engine import Engine
+
+    eng = Engine(device=0, ring_slots=2048)
+    rng = np.random.default_rng(0)
+    vals = (rng.lognormal(np.log(5e6), 0.5, 1001)).astype(np.int64)
+    for i, v in enumerate(vals):
+        eng.phase_host(2, int(v))
+        eng.step_commit(i + 1, 0, 0, 0, 0.0, 0)
+    torch.cuda.synchronize()
+    live = eng.live()
+    med = float(np.median(vals))
+    assert live.phase[2].count == 1001
+    assert live.phase[2].worst_ns == int(vals.max())
+    assert live.phase[2].sum_ns == int(vals.sum())
+    assert abs(live.phase[2].median_ns - med) / med < 0.07
+    eng.close()
+
+
+def test_trace_step_public_api(cuda):
+    """init + trace_step on a tiny model: step numbering, phases, memory, no host sync needed."""
+    import traceml_b200 as traceml
+    from traceml_b200 import runtime
+    from traceml_b200.runtime import reset_trace_session_state
+
+    reset_trace_session_state(0)
+    traceml.init(mode="auto")
+    eng = runtime.get_engine()
+    eng.drain()
+    model = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.ReLU(), torch.nn.Linear(512, 10)).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    ds = torch.utils.data.TensorDataset(torch.randn(64 * 6, 256), torch.randint(0, 10, (64 * 6,)))
+    loader = torch.utils.data.DataLoader(ds, batch_size=64)
+    for x, y in loader:
+        with traceml.trace_step(model):
+            x, y = x.to("cuda"), y.to("cuda")
+            loss = torch.nn.functional.cross_entropy(model(x), y)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    recs, _ = eng.drain()
+    assert list(recs["step"]) == [1, 2, 3, 4, 5, 6]          # first recorded step id is 1
+    assert (recs["n_calls"][:, 0] == 1).all()                 # dataloader_next, flushed with its step
+    assert (recs["n_calls"][:, 1] == 2).all()                 # two H2D copies per step, summed
+    assert (recs["n_calls"][:, 2] == 1).all() and (recs["n_calls"][:, 3] == 1).all()
+    assert (recs["n_calls"][:, 4] == 1).all() and (recs["n_calls"][:, 5] == 1).all()
+    assert (recs["dur_ns"][:, 2:6] > 0).all()
+    assert (recs["gpu_mask"] == 0b011110).all()
+    assert (recs["flags"] == 1).all() and (recs["peak_alloc"] > 0).all()
+    assert (recs["peak_resv"] >= recs["peak_alloc"]).all()
+    # step wall (host clock) contains the device phases' host-side issue time
+    assert (recs["dur_ns"][:, 5] < 5_000_000_000).all()
+
+
+def test_failed_step_flushes_under_old_id(cuda):
+    import traceml_b200 as traceml
+    from traceml_b200 import runtime
+
+    traceml.init(mode="auto")
+    eng = runtime.get_engine()
+    torch.cuda.synchronize()
+    eng.drain()
+    before = runtime.get_trace_session_state().step
+    model = torch.nn.Linear(4, 4).cuda()
+    with pytest.raises(ValueError):
+        with traceml.trace_step(model):
+            raise ValueError("user error")
+    torch.cuda.synchronize()
+    recs, _ = eng.drain()
+    assert runtime.get_trace_session_state().step == before   # not advanced
+    assert len(recs) == 1 and int(recs["step"][0]) == before  # flushed under the old id

@@ -1,0 +1,162 @@
+"""Per-rank runtime: the engine singleton and the sampler agent.
+
+Replaces ``src/traceml/runtime/runtime.py:33-193`` (TraceMLRuntime) and the
+sampler registry's ``run`` profile (``runtime/sampler_registry.py:78-160``):
+one native engine per process/GPU instead of three Python samplers fed by
+queues.  The sampler thread here only drains the host-mapped mirror (no CUDA
+call) and takes the 1 kHz process samples; it never touches the training
+stream.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import threading
+import time
+from typing import Any, Callable, Dict, List, Optional
+
+from .state import TraceSessionState, get_trace_session_state, reset_trace_session_state
+
+_LOCK = threading.Lock()
+_ENGINE = None
+_ENGINE_DEVICE: Optional[int] = None
+
+
+def disabled() -> bool:
+    """TRACEML_DISABLED=1 short-circuits every hook (utils/timing.py:28)."""
+    return os.environ.get("TRACEML_DISABLED", "0") == "1"
+
+
+def summary_window_rows() -> int:
+    try:
+        return max(1, int(os.environ.get("TRACEML_SUMMARY_WINDOW_ROWS", "10000")))
+    except ValueError:
+        return 10_000
+
+
+def _identity():
+    """Global rank / world size without touching CUDA (runtime/identity.py:135-234)."""
+    rank = int(os.environ.get("RANK", "0") or 0)
+    world = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return rank, world
+
+
+def get_engine(device: Optional[int] = None):
+    """The process's engine, created on first use on the current CUDA device.
+
+    Raises if there is no CUDA device or the native library is missing: the
+    B200 engine has no CPU fallback.
+    """
+    global _ENGINE, _ENGINE_DEVICE
+    if _ENGINE is not None and (device is None or device == _ENGINE_DEVICE):
+        return _ENGINE
+    with _LOCK:
+        if _ENGINE is not None and (device is None or device == _ENGINE_DEVICE):
+            return _ENGINE
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "traceml_b200: no CUDA device is visible. The B200-native telemetry engine "
+                "records through CUDA kernels and has no CPU fallback.")
+        from ..engine import Engine
+
+        dev = torch.cuda.current_device() if device is None else int(device)
+        rank, world = _identity()
+        window = summary_window_rows()
+        # reference retention: 1.5 x window rows per rank (reporting/config.py:13-35)
+        slots = int(os.environ.get("TRACEML_RING_SLOTS", str(int(window * 1.5))))
+        if _ENGINE is not None:
+            _ENGINE.close()
+        _ENGINE = Engine(device=dev, rank=rank, world=world, ring_slots=max(1, slots),
+                         proc_slots=max(1, slots))
+        _ENGINE_DEVICE = dev
+        return _ENGINE
+
+
+def shutdown_engine() -> None:
+    global _ENGINE, _ENGINE_DEVICE
+    with _LOCK:
+        if _ENGINE is not None:
+            _ENGINE.close()
+        _ENGINE = None
+        _ENGINE_DEVICE = None
+
+
+class TraceMLRuntime:
+    """Sampler agent: every ``interval`` seconds take one process sample and
+    hand newly completed step records to the registered sinks.
+
+    ``sinks`` are callables ``sink(kind, rows)`` with ``kind`` in
+    {"step_time", "step_memory", "process"} and ``rows`` the reference's wire
+    rows (samplers/schema/*.py) -- this is where the kept TCP publisher /
+    aggregator attaches.
+    """
+
+    def __init__(self, interval_sec: float = 2.0, sinks: Optional[List[Callable]] = None,
+                 sample_process: bool = True):
+        self.interval = max(1e-4, float(interval_sec))
+        self.sinks = list(sinks or [])
+        self.sample_process = sample_process
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+        self._proc = None
+        self.ticks = 0
+        self.steps_seen = 0
+        self.dropped = 0
+
+    def start(self) -> None:
+        if disabled() or self._thread is not None:
+            return
+        from ..samplers import ProcessProbe
+
+        self._proc = ProcessProbe() if self.sample_process else None
+        self._thread = threading.Thread(target=self._loop, name="traceml-b200-sampler", daemon=True)
+        self._thread.start()
+
+    def _tick(self) -> None:
+        from ..samplers import drain_to_wire
+
+        eng = get_engine()
+        if self._proc is not None:
+            self._proc.sample(eng)
+        out = drain_to_wire(eng)
+        self.steps_seen += len(out["step_time"])
+        self.dropped += out["dropped"]
+        self.ticks += 1
+        for sink in self.sinks:
+            for kind in ("step_time", "step_memory", "process"):
+                if out[kind]:
+                    try:
+                        sink(kind, out[kind])
+                    except Exception as exc:  # fail-open (runtime/sender.py:132-139)
+                        print(f"[TraceML] sink failed: {exc}", file=sys.stderr)
+
+    def _loop(self) -> None:
+        while not self._stop.wait(self.interval):
+            try:
+                self._tick()
+            except Exception as exc:
+                print(f"[TraceML] sampler tick failed: {exc}", file=sys.stderr)
+
+    def stop(self) -> None:
+        if self._thread is None:
+            return
+        self._stop.set()
+        self._thread.join(timeout=5.0)
+        self._thread = None
+        try:
+            self._tick()  # final drain (runtime/runtime.py:163-193)
+        except Exception as exc:
+            print(f"[TraceML] final tick failed: {exc}", file=sys.stderr)
+
+
+__all__ = ["TraceMLRuntime", "TraceSessionState", "get_engine", "shutdown_engine", "disabled",
+           "get_trace_session_state", "reset_trace_session_state", "summary_window_rows"]
