@@ -169,6 +169,7 @@ int tml_proc_commit(tml_ctx* ctx, const tml_proc_record* sample, void* stream);
 int tml_proc_drain(tml_ctx* ctx, tml_proc_record* out, uint32_t max_records,
                    uint32_t* n_out, uint64_t* n_dropped);
 uint64_t tml_step_count(tml_ctx* ctx); /* records committed so far */
+uint64_t tml_launch_count(tml_ctx* ctx); /* kernels launched by this context */
 uint64_t tml_proc_count(tml_ctx* ctx);
 
 /* Bulk append of already-formed records from HOST memory (replay, resume,

@@ -133,6 +133,7 @@ SIGNATURES = {
     "tml_proc_drain": (C.c_int, [vp, vp, u32, C.POINTER(u32), C.POINTER(u64)]),
     "tml_step_count": (u64, [vp]),
     "tml_proc_count": (u64, [vp]),
+    "tml_launch_count": (u64, [vp]),
     "tml_ring_load": (C.c_int, [vp, vp, u64, vp]),
     "tml_proc_load": (C.c_int, [vp, vp, u64, vp]),
     "tml_ring_reset": (C.c_int, [vp]),

@@ -685,6 +685,47 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
   }
 }
 
+
+// ------------------------------------------------------------------ K3e: sequential sums
+// Per-rank window means feed rank-level tie-breaks (closest-rank-to-median, argmax)
+// that the reference decides on the last ulp, so for windows up to
+// TML_EXACT_SUM_MAX rows the seven sums are recomputed in the reference's own
+// order -- newest row first, one IEEE add after another (model.py:262-268,
+// alignment.py:59-75) -- by one warp: lane k owns metric k's dependency chain,
+// every lane reads the same row (a broadcast load).  ~10 cycles per row.
+
+#define TML_EXACT_SUM_MAX (1u << 17)
+
+__global__ void __launch_bounds__(32) k_seq_sums(const tml_window_row* __restrict__ rows,
+                                                 const u8* __restrict__ flags, u32 need,
+                                                 long long first, long long last, int aligned,
+                                                 double* __restrict__ out) {
+  const int lane = threadIdx.x;
+  double acc = 0.0;
+  const double2* r2 = reinterpret_cast<const double2*>(rows);
+#pragma unroll 4
+  for (long long i = last; i >= first; --i) {
+    const double2 a = __ldg(&r2[i * 4 + 0]);  // dl, h2d
+    const double2 b = __ldg(&r2[i * 4 + 1]);  // fwd, bwd
+    const double2 c = __ldg(&r2[i * 4 + 2]);  // opt, wall
+    const bool use = flags ? ((flags[i] & need) == need) : true;
+    const double compute = (b.x + b.y) + c.x;
+    const double traced = fmax(c.y, compute);
+    double v;
+    switch (lane) {
+      case 0: v = a.x; break;
+      case 1: v = b.x; break;
+      case 2: v = b.y; break;
+      case 3: v = c.x; break;
+      case 4: v = aligned ? fmax(0.0, traced) : c.y; break;
+      case 5: v = traced; break;
+      default: v = a.x + traced; break;
+    }
+    acc += use ? v : 0.0;  // + 0.0 leaves a non-negative running sum unchanged
+  }
+  if (lane < 7) out[lane] = acc;
+}
+
 // ------------------------------------------------------------------ K4: window reduce
 
 template <int R>
@@ -958,6 +999,7 @@ struct tml_ctx {
   tml_proc_record* h_pmirror = nullptr; tml_proc_record* d_pmirror = nullptr;
   // host-side step state (training thread)
   u64 commits = 0;
+  u64 launches = 0;  // kernels this context has launched (bench: gpu_launches)
   u32 next_slot = 0;
   u64 host_dur[TML_MAX_PHASES] = {0};
   u32 host_calls[TML_MAX_PHASES] = {0};
@@ -1084,6 +1126,7 @@ int tml_phase_begin(tml_ctx* c, uint32_t phase, void* stream) {
   u32 slot = c->next_slot;
   c->next_slot = (slot + 1u) % TML_N_SLOTS;
   k_stamp_begin<<<1, 32, 0, s>>>(c->d_state, slot);
+  c->launches += 1;
   if (cudaPeekAtLastError() != cudaSuccess)
     return set_err(TML_ERR_CUDA, "stamp_begin launch: %s", cudaGetErrorString(cudaGetLastError()));
   return (int)slot;
@@ -1094,6 +1137,7 @@ int tml_phase_end(tml_ctx* c, uint32_t phase, int slot, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (check_capture(s)) return TML_ERR_CAPTURE;
   k_stamp_end<<<1, 32, 0, s>>>(c->d_state, (u32)slot, phase, (u32)(c->commits % TML_N_EPOCHS));
+  c->launches += 1;
   if (cudaPeekAtLastError() != cudaSuccess)
     return set_err(TML_ERR_CUDA, "stamp_end launch: %s", cudaGetErrorString(cudaGetLastError()));
   return TML_OK;
@@ -1137,11 +1181,13 @@ int tml_step_commit(tml_ctx* c, uint64_t step, uint64_t peak_alloc, uint64_t pea
   if (cudaPeekAtLastError() != cudaSuccess)
     return set_err(TML_ERR_CUDA, "commit launch: %s", cudaGetErrorString(cudaGetLastError()));
   c->commits += 1;
+  c->launches += 1;
   c->win_ready = false;
   return TML_OK;
 }
 
 uint64_t tml_step_count(tml_ctx* c) { return c ? c->commits : 0; }
+uint64_t tml_launch_count(tml_ctx* c) { return c ? c->launches : 0; }
 uint64_t tml_proc_count(tml_ctx* c) { return c ? c->proc_commits.load() : 0; }
 
 // ---------------------------------------------------------------- sampler side
@@ -1194,6 +1240,7 @@ int tml_proc_commit(tml_ctx* c, const tml_proc_record* sample, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   k_proc_commit<<<1, 32, 0, s>>>(c->d_state, c->d_pring, c->proc_slots, c->d_pmirror,
                                   c->pmirror_slots, c->d_page, *sample);
+  c->launches += 1;
   if (cudaPeekAtLastError() != cudaSuccess)
     return set_err(TML_ERR_CUDA, "proc_commit launch: %s", cudaGetErrorString(cudaGetLastError()));
   c->proc_commits.fetch_add(1);
@@ -1314,6 +1361,13 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   CK(cudaPeekAtLastError());
   k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, 7, 0u, c->d_final);
   CK(cudaPeekAtLastError());
+  c->launches += 2;
+  if (n - c->win_tstart <= TML_EXACT_SUM_MAX) {  // reference-order sums (overwrite the tree sums)
+    k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, c->d_flags, RF_USABLE | RF_IN_TIME, (long long)c->win_tstart,
+                                (long long)n - 1, 0, c->d_final);
+    CK(cudaPeekAtLastError());
+    c->launches += 1;
+  }
   char* st = (char*)c->h_stage;
   CK(cudaMemcpyAsync(st, c->d_winacc, sizeof(WinAcc), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 256, c->d_final, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1357,6 +1411,7 @@ int tml_win_presence(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, uin
   k_presence<<<grid, 256, 0, s>>>(c->d_steps, c->d_flags, c->win_n, want, glo, span, presence,
                                   c->d_rowof[kind]);
   CK(cudaPeekAtLastError());
+  c->launches += 1;
   return TML_OK;
 }
 
@@ -1389,6 +1444,7 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   k_sel_scatter<<<nb, SEL_THREADS, 0, s>>>(presence, span, c->d_blockcnt, c->d_total, (u64)window,
                                            glo, c->d_rowof[kind], c->d_selrow, c->d_selstep);
   CK(cudaPeekAtLastError());
+  c->launches += 3;
   char* st = (char*)c->h_stage;
   CK(cudaMemcpyAsync(st, c->d_total, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1405,6 +1461,14 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   CK(cudaPeekAtLastError());
   k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
   CK(cudaPeekAtLastError());
+  c->launches += 2;
+  const bool exact = (kind == TML_KIND_TIME) && keep <= TML_EXACT_SUM_MAX;
+  if (exact) {
+    k_seq_sums<<<1, 32, 0, s>>>(c->d_xrows[kind], nullptr, 0u, 0ll, (long long)keep - 1, 1, c->d_final + 16);
+    CK(cudaPeekAtLastError());
+    c->launches += 1;
+    CK(cudaMemcpyAsync(st + 320, c->d_final + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaMemcpyAsync(st + 64, c->d_final, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 256, c->d_selstep, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 264, c->d_selstep + (keep - 1), sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -1415,6 +1479,7 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   out->t_sums[0] = f[0]; out->t_sums[1] = f[4]; out->t_sums[2] = f[5]; out->t_sums[3] = f[8];
   out->t_sums[4] = f[9]; out->t_sums[5] = f[10]; out->t_sums[6] = f[11];
   out->m_sums[0] = f[12]; out->m_sums[1] = f[13]; out->m_sums[2] = f[14]; out->m_sums[3] = f[15];
+  if (exact) memcpy(out->t_sums, st + 320, 7 * sizeof(double));
   memcpy(&out->start_step, st + 256, sizeof(u64));
   memcpy(&out->end_step, st + 264, sizeof(u64));
   out->n_rows = keep;
@@ -1499,6 +1564,7 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
     default: k_window_reduce_any<<<grid, RD_THREADS, 0, s>>>(p); break;
   }
   CK(cudaPeekAtLastError());
+  c->launches += 1;
   return TML_OK;
 }
 
@@ -1516,6 +1582,7 @@ int tml_win_bands(tml_ctx* c, const double* series, const tml_band_args* a, void
   double* d_tail = c->d_partials;        // 32 doubles (scratch)
   k_bands<<<dim3(16, 4), 256, 0, s>>>(p, d_sum, c->d_bandcnt, d_tail);
   CK(cudaPeekAtLastError());
+  c->launches += 1;
   char* st = (char*)c->h_stage;
   CK(cudaMemcpyAsync(st, d_sum, 48 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 512, c->d_bandcnt, 48 * sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -1545,6 +1612,7 @@ int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* o
   CK(cudaPeekAtLastError());
   k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, PR_COLS, PR_MAXMASK, c->d_final);
   CK(cudaPeekAtLastError());
+  c->launches += 2;
   char* st = (char*)c->h_stage;
   CK(cudaMemcpyAsync(st, c->d_final, PR_COLS * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));

@@ -90,6 +90,10 @@ class Engine:
         return int(self._lib.tml_step_count(self._h))
 
     @property
+    def launch_count(self) -> int:
+        return int(self._lib.tml_launch_count(self._h))
+
+    @property
     def proc_count(self) -> int:
         return int(self._lib.tml_proc_count(self._h))
 

@@ -27,6 +27,9 @@ from . import _abi
 
 KIND_TIME, KIND_MEM = _abi.KIND_TIME, _abi.KIND_MEM
 
+_INFO_LEN = 20
+_ALIGN_LEN = 15
+
 # analytics/trends/schema.py:27-62
 _BANDS = ((0.15, 0.25), (0.45, 0.55), (0.90, 1.00))
 _HISTORY_LIMIT = 10_000
@@ -41,6 +44,12 @@ class LocalComm:
 
     def all_gather_obj(self, obj: Any) -> List[Any]:
         return [obj]
+
+    def all_gather_vec(self, vec, device=None) -> List[List[float]]:
+        return [list(vec)]
+
+    def all_gather_bytes(self, blob: bytes, device=None) -> List[bytes]:
+        return [bytes(blob)]
 
     def all_reduce_min_(self, t: torch.Tensor) -> None:
         return None
@@ -67,6 +76,23 @@ class TorchDistComm:
         out: List[Any] = [None] * self.world
         self._dist.all_gather_object(out, obj, group=self.group)
         return out
+
+    def all_gather_vec(self, vec, device=None) -> List[List[float]]:
+        """Fixed-length f64 vectors: one small all-gather, no pickling."""
+        dev = device or torch.device("cpu")
+        inp = torch.tensor(list(vec), dtype=torch.float64, device=dev)
+        out = torch.empty(self.world * inp.numel(), dtype=torch.float64, device=dev)
+        self._dist.all_gather_into_tensor(out, inp, group=self.group)
+        return out.view(self.world, -1).cpu().tolist()
+
+    def all_gather_bytes(self, blob: bytes, device=None) -> List[bytes]:
+        dev = device or torch.device("cpu")
+        inp = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        out = torch.empty(self.world * inp.numel(), dtype=torch.uint8, device=dev)
+        self._dist.all_gather_into_tensor(out, inp, group=self.group)
+        flat = out.cpu().numpy().tobytes()
+        n = len(blob)
+        return [flat[i * n:(i + 1) * n] for i in range(self.world)]
 
     def all_reduce_min_(self, t: torch.Tensor) -> None:
         self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
@@ -178,6 +204,19 @@ class WindowReducer:
             "t_sums": [float(x) for x in w.t_sums], "t_count": int(w.t_count),
         }
 
+    @staticmethod
+    def _info_pack(d: Dict[str, Any]) -> List[float]:
+        return ([d["n_retained"], d["latest_step"], d["monotone"], d["dup_rows"]]
+                + d["n_rows"] + d["n_cand"] + d["lo"] + d["hi"] + d["t_sums"] + [d["t_count"]])
+
+    @staticmethod
+    def _info_unpack(v: Sequence[float]) -> Dict[str, Any]:
+        i = lambda x: int(round(x))  # noqa: E731  (step ids < 2^53)
+        return {"n_retained": i(v[0]), "latest_step": i(v[1]), "monotone": i(v[2]),
+                "dup_rows": i(v[3]), "n_rows": [i(v[4]), i(v[5])], "n_cand": [i(v[6]), i(v[7])],
+                "lo": [i(v[8]), i(v[9])], "hi": [i(v[10]), i(v[11])],
+                "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19])}
+
     def reduce(self, window: int, *, want_series: bool = False) -> ReduceOutput:
         window = max(1, int(window))
         dev = self.device
@@ -191,11 +230,13 @@ class WindowReducer:
 
         # ---- stage 1: local windows + bounds
         local_infos = [self._info_dict(e.win_prepare(window, stream)) for e in self.engines]
-        gathered = self.comm.all_gather_obj(local_infos)
+        flat: List[float] = []
+        for d in local_infos:
+            flat.extend(self._info_pack(d))
         infos: Dict[int, Dict[str, Any]] = {}
-        for p, lst in enumerate(gathered):
-            for l, d in enumerate(lst):
-                infos[p * self.L + l] = d
+        for p, row in enumerate(self.comm.all_gather_vec(flat, dev)):
+            for l in range(self.L):
+                infos[p * self.L + l] = self._info_unpack(row[l * _INFO_LEN:(l + 1) * _INFO_LEN])
         ranks = sorted(infos)
         if ev:
             ev[1].record()
@@ -256,15 +297,20 @@ class WindowReducer:
             e.win_presence(kind, glo, span, p, stream)
             presence = p if presence is None else torch.minimum(presence, p)
         self.comm.all_reduce_min_(presence)
-        aligns = []
+        flat: List[float] = []
         for l, e in enumerate(self.engines):
             a = e.win_select(kind, glo, span, presence, window, stream)
-            aligns.append({
-                "n_common": int(a.n_common), "start": int(a.start_step), "end": int(a.end_step),
-                "n_rows": int(a.n_rows), "t_sums": [float(x) for x in a.t_sums],
-                "m_sums": [float(x) for x in a.m_sums],
-            })
-        gathered = self.comm.all_gather_obj(aligns)
+            flat.extend([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
+                        + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
+        gathered = []
+        for row in self.comm.all_gather_vec(flat, self.device):
+            lst = []
+            for l in range(self.L):
+                v = row[l * _ALIGN_LEN:(l + 1) * _ALIGN_LEN]
+                lst.append({"n_common": int(round(v[0])), "start": int(round(v[1])),
+                            "end": int(round(v[2])), "n_rows": int(round(v[3])),
+                            "t_sums": list(v[4:11]), "m_sums": list(v[11:15])})
+            gathered.append(lst)
         n_common = max(a["n_common"] for lst in gathered for a in lst)
         res.n_common = n_common
         if n_common == 0:
@@ -314,13 +360,14 @@ class WindowReducer:
                 rows[r] = gathered[r * n * 8:(r + 1) * n * 8]
             self._keep = gathered
         else:  # p2p: CUDA-IPC peer mappings, loads fused into the reduce kernel
-            handles = {}
+            blob = b""
             for l in range(self.L):
-                if self._grank(l) in used:
-                    handles[self._grank(l)] = self.engines[l].win_rows_export(kind)
+                blob += (self.engines[l].win_rows_export(kind) if self._grank(l) in used
+                         else bytes(64))
             allh = {}
-            for d in self.comm.all_gather_obj(handles):
-                allh.update(d)
+            for p, b in enumerate(self.comm.all_gather_bytes(blob, dev)):
+                for l in range(self.L):
+                    allh[p * self.L + l] = b[l * 64:(l + 1) * 64]
             e0 = self.engines[0]
             for r in used:
                 if r in my:
@@ -365,13 +412,16 @@ class WindowReducer:
             a.tail_first[0] = 0
             a.tail_first[1] = n - min(n, 1000)
             out = self.engines[0].win_bands(res.series, a, stream)
-            part = {
-                "sum": [[float(out.sum[s][b]) for b in range(3)] for s in range(16)],
-                "cnt": [[int(out.cnt[s][b]) for b in range(3)] for s in range(16)],
-                "tf": [float(out.tail_first[s]) for s in range(16)],
-                "tl": [float(out.tail_last[s]) for s in range(16)],
-            }
-            parts = self.comm.all_gather_obj(part)
+            vec = ([float(out.sum[s][b]) for s in range(16) for b in range(3)]
+                   + [float(out.cnt[s][b]) for s in range(16) for b in range(3)]
+                   + [float(out.tail_first[s]) for s in range(16)]
+                   + [float(out.tail_last[s]) for s in range(16)])
+            parts = []
+            for row in self.comm.all_gather_vec(vec, self.device):
+                parts.append({
+                    "sum": [[row[s * 3 + b] for b in range(3)] for s in range(16)],
+                    "cnt": [[int(round(row[48 + s * 3 + b])) for b in range(3)] for s in range(16)],
+                    "tf": row[96:112], "tl": row[112:128]})
             res.band_sum = [[sum(p["sum"][s][b] for p in parts) for b in range(3)] for s in range(16)]
             res.band_cnt = [[sum(p["cnt"][s][b] for p in parts) for b in range(3)] for s in range(16)]
 

@@ -1,0 +1,202 @@
+"""Bridge from the device-side sections to the KEPT reporting layer.
+
+The reference's payload / card builders and ``FinalReportGenerator`` are kept,
+not rebuilt (``reporting/sections/*/builder.py``,
+``reporting/final.py``).  When the reference package ``traceml`` is importable,
+``to_reference_*`` construct its own dataclasses
+(``StepTimeSectionData`` + ``DiagnosticResult[StepDiagnosis]`` etc.) from our
+section dicts and call its builders, so ``final_summary.json`` /
+``final_summary.txt`` are produced by the unmodified reference code.  Without
+the reference installed, ``build_final_summary`` returns the same numbers in a
+plain envelope (no card text layout of its own).
+"""
+
+from __future__ import annotations
+
+import os
+import socket
+import time
+from typing import Any, Dict, Optional
+
+
+def default_identity(rank: int, world: int) -> Dict[str, Any]:
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)) or world)
+    return {
+        "global_rank": int(rank),
+        "local_rank": int(os.environ.get("LOCAL_RANK", str(rank % max(1, local_world)))),
+        "node_rank": int(os.environ.get("GROUP_RANK", os.environ.get("NODE_RANK", "0")) or 0),
+        "hostname": socket.gethostname(),
+        "local_world_size": local_world,
+        "world_size": int(world),
+    }
+
+
+def reference_available() -> bool:
+    try:
+        import traceml.reporting.sections.step_time.builder  # noqa: F401
+
+        return True
+    except Exception:
+        return False
+
+
+# ----------------------------------------------------------------------------- adapters
+def _issues(items):
+    from traceml.diagnostics.common import DiagnosticIssue
+
+    return tuple(DiagnosticIssue(
+        kind=i["kind"], status=i["status"], severity=i["severity"], summary=i["summary"],
+        action=i["action"], metric=i.get("metric"), phase=i.get("phase"), score=i.get("score"),
+        share_pct=i.get("share_pct"), skew_pct=i.get("skew_pct"),
+        ranks=tuple(int(r) for r in i.get("ranks", ())), evidence=dict(i.get("evidence") or {}))
+        for i in (items or ()))
+
+
+def to_reference_step_time(sec: Dict[str, Any], identities: Dict[int, Dict[str, Any]]):
+    """-> (StepTimeSectionData, Optional[DiagnosticResult[StepDiagnosis]])."""
+    from traceml.diagnostics.common import DiagnosticResult
+    from traceml.diagnostics.step_time.api import StepDiagnosis
+    from traceml.reporting.sections.step_time.alignment import AlignedStepWindow
+    from traceml.reporting.sections.step_time.loader import StepTimeSectionData
+    from traceml.reporting.sections.step_time.model import GlobalRankIdentity, RankStepSummary
+
+    d = sec["data"]
+    mk = lambda s: RankStepSummary(**s)  # noqa: E731
+    ids = {int(r): GlobalRankIdentity(**{k: v.get(k) for k in (
+        "global_rank", "local_rank", "node_rank", "hostname", "local_world_size", "world_size")})
+        for r, v in identities.items()}
+    data = StepTimeSectionData(
+        training_steps=d["training_steps"], latest_step_observed=d["latest_step_observed"],
+        aligned_summary={int(r): mk(s) for r, s in d["aligned_summary"].items()},
+        aligned_step_metrics={}, aligned_window=AlignedStepWindow(**d["aligned_window"]),
+        per_global_rank_summary={int(r): mk(s) for r, s in d["per_global_rank_summary"].items()},
+        per_global_rank_step_metrics={}, identities=ids, max_rows=d["max_rows"])
+    diag = None
+    if sec["diagnosis"] is not None:
+        p = sec["diagnosis"]["primary"]
+        diag = DiagnosticResult(
+            primary=StepDiagnosis(severity=p["severity"], status=p["status"], reason=p["reason"],
+                                  action=p["action"], kind=p["kind"], steps_used=p["steps_used"],
+                                  worst_rank=p["worst_rank"], note=p["note"],
+                                  confidence=p["confidence"]),
+            issues=_issues(sec["diagnosis"]["issues"]),
+            metric_attribution=sec["diagnosis"]["metric_attribution"])
+    return data, diag
+
+
+def to_reference_step_memory(sec: Dict[str, Any], identities: Dict[int, Dict[str, Any]]):
+    from traceml.diagnostics.common import DiagnosticResult
+    from traceml.diagnostics.step_memory import StepMemoryDiagnosis
+    from traceml.renderers.step_memory.schema import (StepMemoryCombinedCoverage,
+                                                      StepMemoryCombinedMetric,
+                                                      StepMemoryCombinedSeries,
+                                                      StepMemoryCombinedSummary)
+    from traceml.reporting.sections.step_memory.loader import StepMemorySectionData
+    from traceml.reporting.sections.step_memory.model import (StepMemoryAlignedWindow,
+                                                              StepMemoryGlobalRankIdentity,
+                                                              StepMemoryGlobalRankSummary)
+
+    def ident(r):
+        v = identities.get(int(r), {"global_rank": int(r)})
+        return StepMemoryGlobalRankIdentity(**{k: v.get(k) for k in (
+            "global_rank", "local_rank", "node_rank", "hostname", "local_world_size", "world_size")})
+
+    metrics = [StepMemoryCombinedMetric(
+        metric=m["metric"], device=None,
+        series=StepMemoryCombinedSeries(steps=[], median=[], worst=[]),
+        summary=StepMemoryCombinedSummary(**m["summary"]),
+        coverage=StepMemoryCombinedCoverage(**m["coverage"])) for m in sec["metrics"]]
+    rows = {k: StepMemoryGlobalRankSummary(identity=ident(k), metrics=dict(v))
+            for k, v in sec["per_global_rank"].items()}
+    w = sec["window"]
+    data = StepMemorySectionData(
+        training_steps=sec["training_steps"], latest_step_observed=sec["latest_step_observed"],
+        metrics=metrics, gpu_total_bytes=sec["gpu_total_bytes"],
+        no_gpu_detected=sec["no_gpu_detected"], per_global_rank=rows,
+        aligned_window=StepMemoryAlignedWindow(steps=(), per_global_rank={},
+                                               window_size=w["window_size"],
+                                               global_ranks_seen=w["global_ranks_seen"]))
+    p = sec["diagnosis"]["primary"]
+    diag = DiagnosticResult(
+        primary=StepMemoryDiagnosis(severity=p["severity"], status=p["status"], reason=p["reason"],
+                                    action=p["action"], kind=p["kind"], metric=p["metric"],
+                                    steps_used=p["steps_used"], worst_rank=p["worst_rank"],
+                                    note=p["note"], confidence=p["confidence"]),
+        issues=_issues(sec["diagnosis"]["issues"]),
+        metric_attribution=sec["diagnosis"]["metric_attribution"])
+    return data, diag
+
+
+def to_reference_process(sec: Dict[str, Any], identities: Dict[int, Dict[str, Any]]):
+    from traceml.diagnostics.common import DiagnosticResult
+    from traceml.diagnostics.process import ProcessDiagnosis
+    from traceml.reporting.sections.process.loader import ProcessSectionData
+    from traceml.reporting.sections.process.model import PerRankProcessSummary, ProcessSummaryAgg
+
+    agg = ProcessSummaryAgg(**sec["aggregate"])
+    per = {}
+    for r, v in sec["per_global_rank"].items():
+        i = identities.get(int(r), {})
+        per[int(r)] = PerRankProcessSummary(
+            local_rank=i.get("local_rank"), world_size=i.get("world_size"),
+            local_world_size=i.get("local_world_size"), node_rank=i.get("node_rank"),
+            hostname=i.get("hostname"), **v)
+    p = sec["primary"]
+    diag = DiagnosticResult(
+        primary=ProcessDiagnosis(severity=p["severity"], status=p["status"], reason=p["reason"],
+                                 action=p["action"], kind=p["kind"], samples_used=p["samples_used"]),
+        issues=_issues(sec["issues"]))
+    return ProcessSectionData(aggregate=agg, per_global_rank=per), diag
+
+
+def reference_payloads(res: Dict[str, Any], identities: Dict[int, Dict[str, Any]]) -> Dict[str, Any]:
+    """Run the KEPT builders: {section: {"payload": ..., "text": ...}}."""
+    from traceml.reporting.sections.process.builder import build_process_payload
+    from traceml.reporting.sections.process.formatter import format_process_section_text
+    from traceml.reporting.sections.step_memory.builder import build_step_memory_section_payload
+    from traceml.reporting.sections.step_memory.formatter import format_step_memory_section_text
+    from traceml.reporting.sections.step_time.builder import build_step_time_payload
+    from traceml.reporting.sections.step_time.formatter import format_step_time_section_text
+
+    out = {}
+    d, g = to_reference_step_time(res["step_time"], identities)
+    p = build_step_time_payload(d, g)
+    out["step_time"] = {"payload": p, "text": format_step_time_section_text(p)}
+    d, g = to_reference_step_memory(res["step_memory"], identities)
+    p = build_step_memory_section_payload(d, g)
+    out["step_memory"] = {"payload": p, "text": format_step_memory_section_text(p)}
+    d, g = to_reference_process(res["process"], identities)
+    p = build_process_payload(d, g)
+    out["process"] = {"payload": p, "text": format_process_section_text(p)}
+    return out
+
+
+def build_final_summary(res: Dict[str, Any], identities: Optional[Dict[int, Dict[str, Any]]] = None
+                        ) -> Dict[str, Any]:
+    """final_summary envelope (reporting/final.py:254-267 key set)."""
+    ranks = res["reduce"].ranks if "reduce" in res else []
+    world = len(ranks) or 1
+    identities = identities or {r: default_identity(r, world) for r in ranks}
+    env: Dict[str, Any] = {"schema_version": "1.2", "generated_at": time.time(),
+                           "engine": "traceml_b200"}
+    if reference_available():
+        sec = reference_payloads(res, identities)
+        for k in ("process", "step_time", "step_memory"):
+            env[k] = sec[k]["payload"]
+        env["text"] = "\n\n".join(sec[k]["text"] for k in ("process", "step_time", "step_memory"))
+    else:
+        for k in ("process", "step_time", "step_memory"):
+            env[k] = {kk: vv for kk, vv in res[k].items()} if isinstance(res[k], dict) else res[k]
+        st = res["step_time"]["diagnosis"]
+        sm = res["step_memory"]["diagnosis"]
+        env["text"] = "\n".join([
+            f"Step Time: {st['primary']['status'] if st else 'NO DATA'}"
+            + (f" -- {st['primary']['reason']}" if st else ""),
+            f"Step Memory: {sm['primary']['status']} -- {sm['primary']['reason']}",
+            f"Process: {res['process']['primary']['status']} -- {res['process']['primary']['reason']}",
+        ])
+    return env
+
+
+__all__ = ["build_final_summary", "reference_payloads", "reference_available", "default_identity",
+           "to_reference_step_time", "to_reference_step_memory", "to_reference_process"]
