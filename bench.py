@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200.
+
+BASELINE.json metric: "per-step profiling overhead (us) at 1/2/4/8 ranks;
+cross-rank reduce GB/s".  One invocation measures both legs:
+
+  reduce leg   (``metric``/``value``/``roofline``/``e2e``)
+      workload = BASELINE config 4's NVLink-reduce stress replay: every rank holds
+      W step records (default W = 4e6 ~ 1 kHz x 67 min) plus 60 000 process samples.
+      A "step" is one full cross-rank window reduce (align -> exchange -> per-step
+      median/worst -> trend bands -> process aggregates -> rule engines).
+      value = algorithmic bytes B_reduce(R, W) = R*W*64 + 128*W + 72*R per step / time,
+      records resident in HBM.  e2e = same, but each step starts from HOST (pinned)
+      StepRecord buffers: H2D of W*128 B per rank + reduce + results back on the host.
+  step leg     (``step_overhead``)
+      BASELINE config 2: synthetic ResNet-18 (batch 64x3x224x224, DDP when N > 1)
+      and the isolated tiny-MLP micro-harness; per-step wall of untraced vs traced
+      (this engine, auto mode) vs the reference's timer path (oracle port).
+
+``--impl reference`` runs the reference's own CPU algorithm (the oracle port --
+the reference is pure Python and cannot travel to the GPU box) on a bounded
+sample of the same workload, rank 0 only.
+
+Launch: ``python bench.py --gpus N --steps K --warmup W`` (N = 1) or under
+``python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def b_reduce(R: int, W: int) -> float:
+    """Algorithmic bytes of one window reduce."""
+    return float(R) * W * 64.0 + 128.0 * W + 72.0 * R
+
+
+def dist_setup():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def max_over_ranks(x: float, world: int, device) -> float:
+    if world <= 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- models
+def resnet18(num_classes=10):
+    import torch.nn as nn
+
+    class Block(nn.Module):
+        def __init__(self, cin, cout, stride):
+            super().__init__()
+            self.c1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False); self.b1 = nn.BatchNorm2d(cout)
+            self.c2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False); self.b2 = nn.BatchNorm2d(cout)
+            self.down = None
+            if stride != 1 or cin != cout:
+                self.down = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+        def forward(self, x):
+            y = torch.relu(self.b1(self.c1(x)))
+            y = self.b2(self.c2(y))
+            return torch.relu(y + (x if self.down is None else self.down(x)))
+
+    layers = [nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(), nn.MaxPool2d(3, 2, 1)]
+    cin = 64
+    for cout, stride in ((64, 1), (64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 2), (512, 1)):
+        layers.append(Block(cin, cout, stride)); cin = cout
+    layers += [nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(512, num_classes)]
+    return nn.Sequential(*layers)
+
+
+def step_overhead(device, world, local, quick=False):
+    """Per-step wall: untraced vs this engine (auto mode) vs the reference timer path."""
+    import traceml_b200 as traceml
+    from oracle.timer_oracle import ReferenceTimerPath  # cpu_baseline leg only
+
+    traceml.init(mode="auto")
+    ref = ReferenceTimerPath()
+    out = {}
+
+    def run_arm(arm, model, opt, xs, ys, n):
+        lossf = torch.nn.functional.cross_entropy
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for i in range(n):
+            x, y = xs[i % len(xs)], ys[i % len(ys)]
+            if arm == "untraced":
+                xd, yd = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+                loss = lossf(model(xd), yd); loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
+            elif arm == "b200":
+                with traceml.trace_step(model):
+                    xd, yd = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+                    loss = lossf(model(xd), yd); loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
+            else:  # reference timer path (oracle port), phases wrapped by hand
+                with ref.trace_step(model):
+                    with ref.timed_region("_traceml_internal:h2d_time"):
+                        xd = x.to(device, non_blocking=True)
+                    with ref.timed_region("_traceml_internal:h2d_time"):
+                        yd = y.to(device, non_blocking=True)
+                    with ref.timed_region("_traceml_internal:forward_time"):
+                        loss = lossf(model(xd), yd)
+                    with ref.timed_region("_traceml_internal:backward_time"):
+                        loss.backward()
+                    with ref.timed_region("_traceml_internal:optimizer_step"):
+                        opt.step()
+                    opt.zero_grad(set_to_none=True)
+                if i % 64 == 63:
+                    ref.sample()  # the sampler thread's work, amortised
+        torch.cuda.synchronize(device)
+        if arm == "reference":
+            ref.sample()
+        return (time.perf_counter() - t0) / n * 1.0e6
+
+    def harness(name, model, xs, ys, n, cycles):
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+        for arm in ("untraced", "b200", "reference"):
+            run_arm(arm, model, opt, xs, ys, max(5, n // 4))  # warm-up
+        res = {"untraced": [], "b200": [], "reference": []}
+        for _ in range(cycles):
+            for arm in res:
+                res[arm].append(run_arm(arm, model, opt, xs, ys, n))
+        base = statistics.median(res["untraced"])
+        out[name] = {
+            "untraced_us": base,
+            "b200_us": statistics.median(res["b200"]),
+            "reference_us": statistics.median(res["reference"]),
+            "b200_overhead_us": statistics.median(res["b200"]) - base,
+            "reference_overhead_us": statistics.median(res["reference"]) - base,
+            "steps_per_cycle": n, "cycles": cycles,
+        }
+
+    torch.manual_seed(0)
+    mlp = torch.nn.Linear(8, 8).to(device)
+    xs = [torch.randn(16, 8).pin_memory() for _ in range(8)]
+    ys = [torch.randint(0, 8, (16,)).pin_memory() for _ in range(8)]
+    harness("micro_mlp", mlp, xs, ys, 100 if quick else 400, 3 if quick else 5)
+
+    model = resnet18().to(device)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    xs = [torch.randn(64, 3, 224, 224).pin_memory() for _ in range(2)]
+    ys = [torch.randint(0, 10, (64,)).pin_memory() for _ in range(2)]
+    harness("resnet18_b64", model, xs, ys, 8 if quick else 24, 2 if quick else 3)
+    return out
+
+
+# ----------------------------------------------------------------------------- reference arm
+def oracle_reduce_sample(R: int, W: int, seed: int = 1):
+    """Time the oracle (port of the reference's CPU reduce) on R ranks x W rows."""
+    from helpers import oracle_mem_rows, oracle_proc_rows, oracle_time_rows
+    from oracle import process_oracle, step_memory_oracle, step_time_oracle
+    from traceml_b200 import replay
+
+    recs = replay.make_step_replay("balanced", R, W, seed)
+    procs = replay.make_proc_replay("normal", R, 2000, seed)
+    trows, mrows, prows = oracle_time_rows(recs, W), oracle_mem_rows(recs), oracle_proc_rows(procs, R)
+
+    def once():
+        t0 = time.perf_counter()
+        step_time_oracle.step_time_section(trows, max_rows=W)
+        step_memory_oracle.step_memory_section(mrows, window_size=W)
+        process_oracle.process_section(prows, max_rows=W)
+        return time.perf_counter() - t0
+
+    return once
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    R = max(1, args.gpus)
+    Ws = args.sample
+    once = oracle_reduce_sample(R, Ws)
+    for _ in range(max(1, min(args.warmup, 1))):
+        once()
+    times = [once() for _ in range(max(1, min(args.steps, 5)))]
+    t = statistics.median(times)
+    val = b_reduce(R, Ws) / t / 1e9
+    line = {
+        "impl": "reference", "metric": "cross_rank_reduce_GBps", "value": val, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"reduce-stress replay sample: R={R} ranks x W={Ws} steps (oracle port, "
+                               "rows already parsed: no SQLite/JSON)"},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": "port",
+                         "sample": f"R={R} x W={Ws} rows, median of {len(times)}; {t / (R * Ws) * 1e6:.1f} us/row"},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": os.cpu_count(),
+    }
+    if torch.cuda.is_available() and not args.no_overhead:
+        try:
+            line["step_overhead"] = step_overhead(torch.device("cuda", 0), 1, 0, quick=True)
+        except Exception as exc:
+            line["step_overhead"] = {"error": str(exc)}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--window", type=int, default=4_000_000, help="W: step records per rank")
+    ap.add_argument("--sample", type=int, default=40_000, help="cpu-baseline rows per rank")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--no-overhead", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+
+    rank, local, world = dist_setup()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from traceml_b200 import replay, sections
+    from traceml_b200.engine import Engine
+    from traceml_b200.reduce import LocalComm, TorchDistComm
+
+    W = int(args.window)
+    R = world
+    comm = TorchDistComm() if world > 1 else LocalComm()
+
+    # ---- synthetic inputs of BASELINE config 4's shape, one rank's worth, in pinned host memory
+    recs = replay.make_step_replay("balanced", R, W, seed=1, only_ranks=[rank])[rank]
+    procs = replay.make_proc_replay("normal", R, 60_000, seed=1, only_ranks=[rank])[rank]
+    host = torch.empty(W * 128, dtype=torch.uint8).pin_memory()
+    host.numpy()[:] = recs.view(np.uint8).reshape(-1)
+    del recs
+    eng = Engine(device=local, rank=rank, world=R, ring_slots=W, proc_slots=65_536)
+    eng.load_procs(procs)
+    stream = torch.cuda.current_stream(device)
+    eng.load_steps_ptr(host.data_ptr(), W, stream.cuda_stream)
+    torch.cuda.synchronize(device)
+    summ = sections.SummaryEngine([eng], comm, exchange=args.exchange,
+                                  ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=R)
+
+    # ---- (1) device-resident reduce: K steps, CUDA events, max over ranks
+    for _ in range(args.warmup):
+        res = summ.build(W, 60_000)
+    clocks = ClockSampler(local)
+    barrier(world); torch.cuda.synchronize(device)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {}
+    e0.record()
+    for _ in range(args.steps):
+        res = summ.build(W, 60_000)
+        for k, v in res["reduce"].timings_ms.items():
+            stage.setdefault(k, []).append(v)
+    e1.record()
+    torch.cuda.synchronize(device); barrier(world)
+    launches = eng.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
+    ms_step = ms_total / args.steps
+    value = b_reduce(R, W) / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernels (per launch, this rank)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as fh:
+            peak = float(json.load(fh)["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst)"
+    med = {k: statistics.median(v) for k, v in stage.items()}
+    n_shard = W // R
+    k4_bytes = R * n_shard * 64.0 + 128.0 * n_shard          # rows read + 16 series written
+    k3a_bytes = W * (128.0 + 64.0 + 8.0 + 1.0)               # record read, row + step id + flags written
+    kernels = {
+        "k_window_reduce": {"ms": med.get("k4"), "bytes": k4_bytes,
+                            "GBps": k4_bytes / (med["k4"] * 1e-3) / 1e9 if med.get("k4") else None},
+        "k_window_rows": {"ms": med.get("k3a"), "bytes": k3a_bytes,
+                          "GBps": k3a_bytes / (med["k3a"] * 1e-3) / 1e9 if med.get("k3a") else None},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]["ms"] or 0.0)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak,
+                "unit": "GB/s", "frac": (kernels[dom]["GBps"] or 0.0) / peak, "traffic": None,
+                "peak_source": peak_src, "kernels": kernels, "stage_ms": med}
+
+    # ---- (2) end to end from HOST buffers: H2D + reduce + results on the host
+    def e2e_once():
+        eng.reset()
+        eng.load_procs(procs)
+        eng.load_steps_ptr(host.data_ptr(), W, stream.cuda_stream)
+        return summ.build(W, 60_000)
+
+    for _ in range(2):
+        e2e_once()
+    barrier(world); torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_once()
+    torch.cuda.synchronize(device)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, device) / args.steps
+    barrier(world)
+    e2e = {"value": b_reduce(R, W) / e2e_s / 1e9, "unit": "GB/s",
+           "h2d_bytes_per_step": (W * 128 + 60_000 * 64) * R, "d2h_bytes_per_step": 2_200 * R,
+           "ms_per_step": e2e_s * 1e3}
+
+    # ---- (3) per-step overhead leg
+    overhead = None
+    if not args.no_overhead:
+        eng.close()
+        overhead = step_overhead(device, world, local)
+
+    # ---- (4) CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        once = oracle_reduce_sample(1, args.sample)
+        once()
+        t = once()
+        cpu = {"value": b_reduce(1, args.sample) / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+               "sample": f"R=1 x W={args.sample} rows ({t:.2f} s, {t / args.sample * 1e6:.1f} us/row); "
+                         "oracle port of the reference's Python reduce, rows pre-parsed (no SQLite/JSON)",
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        st = res["step_time"]["diagnosis"]
+        line = {
+            "metric": "cross_rank_reduce_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4 reduce-stress replay: R={R} ranks x W={W} step "
+                                   "records/rank (128 B) + 60000 process samples/rank; full window "
+                                   "reduce + diagnosis per step",
+                       "window": W, "ranks": R, "exchange": res["reduce"].exchange,
+                       "l2": "inputs larger than L2 (ring 512 MB/rank at W=4e6); no flush needed",
+                       "algorithmic_bytes_per_step": b_reduce(R, W)},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "step_overhead": overhead,
+            "diagnosis": st["primary"]["status"] if st else None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -189,6 +189,7 @@ class WindowReducer:
         self.L = len(self.engines)
         self.exchange = exchange
         self._series_cache: Dict[int, torch.Tensor] = {}
+        self._k4_events: List[Any] = []
 
     # global rank of local engine l
     def _grank(self, l: int) -> int:
@@ -221,6 +222,7 @@ class WindowReducer:
         window = max(1, int(window))
         dev = self.device
         stream = _stream_of(dev)
+        self._k4_events = []
         R = self.comm.world * self.L
         ev = None
         timings: Dict[str, float] = {}
@@ -273,6 +275,8 @@ class WindowReducer:
             for i, nm in enumerate(names):
                 timings[nm] = float(ev[i].elapsed_time(ev[i + 1]))
             timings["total"] = float(ev[0].elapsed_time(ev[4]))
+            timings["k3a"] = timings["prepare"]
+            timings["k4"] = float(sum(a.elapsed_time(b) for a, b in self._k4_events))
         if not want_series:
             pass
         return ReduceOutput(window=window, ranks=ranks, infos=infos, time=t_res, mem=m_res,
@@ -378,6 +382,10 @@ class WindowReducer:
         # step-sharded: shard s of W_total shards -> engine with global rank s
         W = self.comm.world * self.L
         lo_first, hi_last = None, None
+        timed = self.device.type == "cuda"
+        if timed:
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
         for l, e in enumerate(self.engines):
             g = self._grank(l)
             lo = (n * g) // W
@@ -387,6 +395,9 @@ class WindowReducer:
             hi_last = hi
             if hi > lo:
                 e.win_reduce([rows[r] for r in used], mask, n, lo, hi, series, stream)
+        if timed:
+            k1.record()
+            self._k4_events.append((k0, k1))
         res.series = series.view(_abi.TML_SERIES_PER_STEP, n)
         res.shard = (lo_first or 0, hi_last or 0)
         if mode == "p2p":

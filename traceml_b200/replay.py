@@ -59,12 +59,14 @@ def make_step_replay(
     n_steps: int,
     seed: int = 0,
     first_step: int = 1,
+    only_ranks=None,
 ) -> Dict[int, np.ndarray]:
-    """Return ``{rank: StepRecord[n]}`` for one named scenario."""
+    """Return ``{rank: StepRecord[n]}`` for one named scenario (``only_ranks``
+    restricts generation to some ranks of the same n_ranks-wide job)."""
     if scenario not in STEP_SCENARIOS:
         raise ValueError(f"unknown step scenario {scenario!r}")
     out: Dict[int, np.ndarray] = {}
-    for rank in range(n_ranks):
+    for rank in (range(n_ranks) if only_ranks is None else only_ranks):
         rng = np.random.default_rng([int(seed), int(rank), 0xB200])
         n = int(n_steps)
         if scenario == "warmup":
@@ -155,12 +157,13 @@ def make_proc_replay(
     n_samples: int,
     seed: int = 0,
     period_s: float = 0.001,
+    only_ranks=None,
 ) -> Dict[int, np.ndarray]:
     """Return ``{rank: ProcRecord[n]}`` (1 kHz by default -- BASELINE config 4)."""
     if scenario not in PROC_SCENARIOS:
         raise ValueError(f"unknown process scenario {scenario!r}")
     out: Dict[int, np.ndarray] = {}
-    for rank in range(n_ranks):
+    for rank in (range(n_ranks) if only_ranks is None else only_ranks):
         rng = np.random.default_rng([int(seed), int(rank), 0x9C])
         n = int(n_samples)
         rec = np.zeros(n, dtype=PROC_RECORD_DTYPE)
