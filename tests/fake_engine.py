@@ -1,0 +1,160 @@
+"""numpy test double of the engine's reduce stages (TEST INFRASTRUCTURE).
+
+Implements the same stage contract as ``traceml_b200.engine.Engine`` on CPU
+tensors so the multi-process orchestration in ``traceml_b200.reduce`` /
+``sections`` (collectives, sharding, partial-sum merging) can run under
+``gloo`` with world_size 2 on a box without a GPU.  It is NOT a fallback: the
+product never imports it.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+RF_USABLE, RF_HAS_MEM, RF_IN_TIME, RF_CAND_T, RF_CAND_M = 1, 2, 4, 8, 16
+
+
+class FakeEngine:
+    def __init__(self, records, procs=None, device=0):
+        self.records = records
+        self.procs = procs
+        self.device = device
+        self.xrows = {0: None, 1: None}
+
+    # ---- stage 1
+    def win_prepare(self, window, stream=0):
+        r = self.records
+        n = len(r)
+        self.n = n
+        self.t_start = max(0, n - window)
+        ms = r["dur_ns"].astype(np.float64) / 1.0e6
+        self.rows = np.zeros((n, 8))
+        self.rows[:, :6] = ms
+        self.rows[:, 6] = r["peak_alloc"].astype(np.float64)
+        self.rows[:, 7] = r["peak_resv"].astype(np.float64)
+        self.steps = r["step"].astype(np.int64)
+        usable = (ms[:, [0, 2, 3, 4, 5]] > 0).any(axis=1) if n else np.zeros(0, bool)
+        has_mem = (r["flags"] & 1) != 0
+        idx = np.arange(n)
+        in_time = idx >= self.t_start
+        prev_diff = np.ones(n, bool)
+        prev_diff[1:] = self.steps[1:] != self.steps[:-1]
+        first = prev_diff | (idx == self.t_start)
+        nxt_diff = np.ones(n, bool)
+        if n > 1:
+            nxt_diff[:-1] = (self.steps[1:] != self.steps[:-1]) | (~has_mem[1:])
+        self.cand = {0: usable & in_time & first, 1: has_mem & nxt_diff}
+        sel = usable & in_time
+        fwd, bwd, opt, wall, dl = ms[:, 2], ms[:, 3], ms[:, 4], ms[:, 5], ms[:, 0]
+        comp = (fwd + bwd) + opt
+        traced = np.maximum(wall, comp)
+        sums = [0.0] * 7
+        for i in range(n - 1, self.t_start - 1, -1):  # reference order
+            if sel[i]:
+                for k, v in enumerate((dl[i], fwd[i], bwd[i], opt[i], wall[i], traced[i], dl[i] + traced[i])):
+                    sums[k] += v
+        out = SimpleNamespace(
+            n_retained=n, latest_step=int(self.steps.max()) if n else 0, monotone=1,
+            dup_rows=int((~prev_diff).sum()) if n else 0,
+            n_rows=[int(in_time.sum()), int(has_mem.sum())],
+            n_cand=[int(self.cand[0].sum()), int(self.cand[1].sum())],
+            lo=[int(self.steps[self.cand[k]].min()) if self.cand[k].any() else 0 for k in (0, 1)],
+            hi=[int(self.steps[self.cand[k]].max()) if self.cand[k].any() else 0 for k in (0, 1)],
+            t_sums=sums, t_count=int(sel.sum()))
+        return out
+
+    # ---- stage 2
+    def win_presence(self, kind, glo, span, presence, stream=0):
+        if self.n == 0 or not self.cand[kind].any():
+            presence.fill_(1)
+            return
+        presence.zero_()
+        self.rowof = {} if not hasattr(self, "rowof") else self.rowof
+        rowof = np.full(span, -1, dtype=np.int64)
+        for i in np.nonzero(self.cand[kind])[0]:
+            s = int(self.steps[i]) - glo
+            if 0 <= s < span:
+                presence[s] = 1
+                rowof[s] = i
+        self.rowof[kind] = rowof
+
+    # ---- stage 3
+    def win_select(self, kind, glo, span, presence, window, stream=0):
+        p = presence.numpy().astype(bool)
+        idx = np.nonzero(p)[0][-window:]
+        out = SimpleNamespace(n_common=len(idx), start_step=0, end_step=0, n_rows=0,
+                              t_sums=[0.0] * 7, m_sums=[0.0] * 4)
+        if len(idx) == 0 or self.n == 0 or not self.cand[kind].any():
+            self.xrows[kind] = None
+            return out
+        rows = self.rows[self.rowof[kind][idx]]
+        self.xrows[kind] = rows.copy()
+        dl, fwd, bwd, opt, wall = rows[:, 0], rows[:, 2], rows[:, 3], rows[:, 4], rows[:, 5]
+        comp = (fwd + bwd) + opt
+        traced = np.maximum(wall, comp)
+        sums = [0.0] * 7
+        for j in range(len(idx) - 1, -1, -1):
+            for k, v in enumerate((dl[j], fwd[j], bwd[j], opt[j], max(0.0, traced[j]), traced[j], dl[j] + traced[j])):
+                sums[k] += v
+        out.t_sums = sums
+        out.m_sums = [float(rows[:, 6].sum()), float(rows[:, 7].sum()),
+                      float(rows[:, 6].max()), float(rows[:, 7].max())]
+        out.start_step, out.end_step, out.n_rows = int(glo + idx[0]), int(glo + idx[-1]), len(idx)
+        return out
+
+    def win_rows_tensor(self, kind, n):
+        if self.xrows[kind] is None:
+            return torch.zeros(n * 8, dtype=torch.float64)
+        return torch.from_numpy(self.xrows[kind].reshape(-1).copy())
+
+    # ---- stage 4
+    def win_reduce(self, rows, mask, n, lo, hi, series, stream=0):
+        R = len(rows)
+        a = np.stack([r.numpy().reshape(n, 8)[lo:hi] for r in rows])  # [R, m, 8]
+        dl, fwd, bwd, opt, wall = a[..., 0], a[..., 2], a[..., 3], a[..., 4], a[..., 5]
+        comp = (fwd + bwd) + opt
+        traced = np.maximum(wall, comp)
+        wait = np.maximum(0.0, traced - comp)
+        S = series.numpy().reshape(16, n)
+        mets = [dl, fwd, bwd, opt, traced, wait, a[..., 6], a[..., 7]]
+        for mi, v in enumerate(mets):
+            if (mi < 6 and not mask & 1) or (mi >= 6 and not mask & 2):
+                continue
+            srt = np.sort(v, axis=0)
+            med = srt[R // 2] if R % 2 else (srt[R // 2 - 1] + srt[R // 2]) * 0.5
+            S[2 * mi, lo:hi] = med
+            S[2 * mi + 1, lo:hi] = srt[-1]
+
+    # ---- stage 5
+    def win_bands(self, series, args, stream=0):
+        n = int(args.n_common)
+        S = series.numpy().reshape(16, n)
+        lo_s, hi_s = int(args.shard_lo), int(args.shard_hi)
+        out = SimpleNamespace(sum=[[0.0] * 3 for _ in range(16)], cnt=[[0] * 3 for _ in range(16)],
+                              tail_first=[float("nan")] * 16, tail_last=[float("nan")] * 16)
+        for s in range(16):
+            k = 1 if s >= 12 else 0
+            for b in range(3):
+                lo, hi = max(int(args.band_lo[k][b]), lo_s), min(int(args.band_hi[k][b]), hi_s)
+                if hi > lo:
+                    out.sum[s][b] = float(S[s, lo:hi].sum())
+                    out.cnt[s][b] = hi - lo
+            f, l = int(args.tail_first[k]), n - 1
+            if n and lo_s <= f < hi_s:
+                out.tail_first[s] = float(S[s, f])
+            if n and lo_s <= l < hi_s:
+                out.tail_last[s] = float(S[s, l])
+        return out
+
+    def proc_reduce(self, max_rows, stream=0):
+        from test_native_diag_cpu import _agg_from_records
+
+        if self.procs is None:
+            from traceml_b200 import _abi
+
+            a = _abi.ProcAgg()
+            a.max_ratio = -1.0
+            return a
+        return _agg_from_records(self.procs, max_rows)

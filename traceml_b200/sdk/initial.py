@@ -62,13 +62,24 @@ def _build(mode, overrides, source) -> TraceMLInitConfig:
     return TraceMLInitConfig("selective", source=source, **vals)
 
 
+def _require_engine() -> None:
+    """Fail at init, loudly, when the native engine cannot run here."""
+    from .. import _abi
+
+    _abi.lib()  # ImportError if libtraceml_b200.so is missing or stale
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "traceml_b200.init(): no CUDA device is visible. The B200-native engine records "
+            "through CUDA kernels and has no CPU fallback; set TRACEML_DISABLED=1 to run untraced.")
+
+
 def _apply(cfg: TraceMLInitConfig) -> None:
     from ..runtime import disabled
 
     if not disabled():
-        from .. import _abi
-
-        _abi.lib()  # fail now if the native engine is missing
+        _require_engine()
     if not any(getattr(cfg, f) for f in _PATCH_FIELDS):
         return
     try:
