@@ -208,6 +208,35 @@ def step_overhead(device, world, local, quick=False):
             "steps_per_cycle": n, "cycles": cycles,
         }
 
+    # raw per-call host cost of the step-path entry points (tight loops, sync at the end)
+    try:
+        from traceml_b200 import runtime as _rt
+
+        eng = _rt.get_engine()
+        h, sp = eng._h, torch.cuda.current_stream(device).cuda_stream
+        n = 3000
+
+        def cost(fn):
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            dt = (time.perf_counter() - t0) / n * 1e6
+            torch.cuda.synchronize(device)
+            return dt
+
+        ev_pool = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        out["api_cost_us"] = {
+            "begin_end_pair": cost(lambda: eng._end(h, 2, eng._begin(h, 2, sp), sp)),
+            "phase_host": cost(lambda: eng._host(h, 5, 1000)),
+            "step_commit": cost(lambda: eng._commit(h, 1, 0, 0, 0, 0.0, sp)),
+            "cuda_event_record_pair": cost(lambda: (ev_pool[0].record(), ev_pool[1].record())),
+            "empty_lambda": cost(lambda: None),
+        }
+        eng.drain()
+    except Exception as exc:
+        out["api_cost_us"] = {"error": str(exc)}
+
     torch.manual_seed(0)
     mlp = torch.nn.Linear(8, 8).to(device)
     xs = [torch.randn(16, 8).pin_memory() for _ in range(8)]

@@ -203,6 +203,9 @@ typedef struct tml_win_info {
    * step_cpu(raw), traced, total; and the row count n                        */
   double t_sums[7];
   uint64_t t_count;
+  /* rows that are candidates of BOTH kinds: n_both == n_cand[0] == n_cand[1]
+   * means the time and memory candidate sets are the same rows               */
+  uint64_t n_both;
 } tml_win_info;
 
 /* Stage 1 (local).  Linearises the ring into WindowRows (ns -> ms), step ids

@@ -86,15 +86,22 @@ def test_wrappers_refuse_to_stack_on_auto_patches(monkeypatch):
 
 
 def test_disabled_short_circuits_everything(monkeypatch):
-    monkeypatch.setenv("TRACEML_DISABLED", "1")
-    from traceml_b200.sdk.instrumentation import trace_step
-    from traceml_b200.utils.timing import timed_region
+    from traceml_b200 import runtime
 
-    ran = []
-    with trace_step(nn.Linear(2, 2)):
-        with timed_region("_traceml_internal:forward_time"):
-            ran.append(1)
-    assert ran == [1]
+    monkeypatch.setenv("TRACEML_DISABLED", "1")
+    runtime.refresh_disabled()
+    try:
+        from traceml_b200.sdk.instrumentation import trace_step
+        from traceml_b200.utils.timing import timed_region
+
+        ran = []
+        with trace_step(nn.Linear(2, 2)):
+            with timed_region("_traceml_internal:forward_time"):
+                ran.append(1)
+        assert ran == [1]
+    finally:
+        monkeypatch.delenv("TRACEML_DISABLED")
+        runtime.refresh_disabled()
 
 
 def test_forward_targets_include_ddp_and_fsdp_inner():

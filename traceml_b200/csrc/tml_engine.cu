@@ -101,6 +101,7 @@ struct WinAcc {  // integer side results of k_window_rows (atomics; order-indepe
   u64 violations;
   u64 dups;
   u64 t_count;
+  u64 n_both;  // rows that are candidates of BOTH kinds (time == memory window test)
 };
 
 // ------------------------------------------------------------------ device helpers
@@ -343,14 +344,11 @@ __global__ void __launch_bounds__(WR_THREADS) k_window_rows(
   uint4* const s_out = s_in;               // rows leave through the same buffer (16 KB used)
   __shared__ u64 s_steps[WR_THREADS + 2];
   __shared__ u8 s_hasmem[WR_THREADS + 2];
-  __shared__ u64 s_lo[2], s_hi[2], s_ncand[2], s_nrows[2], s_latest, s_viol, s_dups, s_tcount;
-
+  // integer side results: per-thread registers over the persistent loop, one
+  // warp-shuffle + shared-memory reduction per block at the end (no atomics in the loop)
+  u64 a_lo0 = ~0ull, a_lo1 = ~0ull, a_hi0 = 0, a_hi1 = 0, a_latest = 0;
+  u32 a_nc0 = 0, a_nc1 = 0, a_nr0 = 0, a_nr1 = 0, a_viol = 0, a_dups = 0, a_tc = 0, a_both = 0;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    s_lo[0] = s_lo[1] = ~0ull; s_hi[0] = s_hi[1] = 0ull;
-    s_ncand[0] = s_ncand[1] = 0ull; s_nrows[0] = s_nrows[1] = 0ull;
-    s_latest = 0ull; s_viol = 0ull; s_dups = 0ull; s_tcount = 0ull;
-  }
   double sums[7] = {0, 0, 0, 0, 0, 0, 0};
   const u64 ntiles = (n + WR_THREADS - 1) / WR_THREADS;
   const uint4* ring4 = reinterpret_cast<const uint4*>(ring);
@@ -432,20 +430,21 @@ __global__ void __launch_bounds__(WR_THREADS) k_window_rows(
       steps[i] = step;
       flags[i] = f;
 
-      atomicMax(&s_latest, step);
-      if (has_prev && step < prev_step) atomicAdd(&s_viol, 1ull);
-      if (has_prev && step == prev_step) atomicAdd(&s_dups, 1ull);
-      if (in_time) atomicAdd(&s_nrows[0], 1ull);
-      if (has_mem) atomicAdd(&s_nrows[1], 1ull);
-      if (cand_t) { atomicMin(&s_lo[0], step); atomicMax(&s_hi[0], step); atomicAdd(&s_ncand[0], 1ull); }
-      if (cand_m) { atomicMin(&s_lo[1], step); atomicMax(&s_hi[1], step); atomicAdd(&s_ncand[1], 1ull); }
+      a_latest = step > a_latest ? step : a_latest;
+      a_viol += (has_prev && step < prev_step) ? 1u : 0u;
+      a_dups += (has_prev && step == prev_step) ? 1u : 0u;
+      a_nr0 += in_time ? 1u : 0u;
+      a_nr1 += has_mem ? 1u : 0u;
+      if (cand_t) { a_lo0 = step < a_lo0 ? step : a_lo0; a_hi0 = step > a_hi0 ? step : a_hi0; ++a_nc0; }
+      if (cand_m) { a_lo1 = step < a_lo1 ? step : a_lo1; a_hi1 = step > a_hi1 ? step : a_hi1; ++a_nc1; }
+      a_both += (cand_t && cand_m) ? 1u : 0u;
 
       if (usable && in_time) {  // model.py:241-271, same expression order
         const double compute = (fwd + bwd) + opt;
         const double traced = fmax(wall, compute);
         sums[0] += dl; sums[1] += fwd; sums[2] += bwd; sums[3] += opt;
         sums[4] += wall; sums[5] += traced; sums[6] += dl + traced;
-        atomicAdd(&s_tcount, 1ull);
+        ++a_tc;
       }
 
       // row -> swizzled staging (4 x 16 B)
@@ -468,15 +467,33 @@ __global__ void __launch_bounds__(WR_THREADS) k_window_rows(
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    atomicMin(&acc->lo[0], s_lo[0]); atomicMin(&acc->lo[1], s_lo[1]);
-    atomicMax(&acc->hi[0], s_hi[0]); atomicMax(&acc->hi[1], s_hi[1]);
-    atomicAdd(&acc->ncand[0], s_ncand[0]); atomicAdd(&acc->ncand[1], s_ncand[1]);
-    atomicAdd(&acc->nrows[0], s_nrows[0]); atomicAdd(&acc->nrows[1], s_nrows[1]);
-    atomicMax(&acc->latest_step, s_latest);
-    atomicAdd(&acc->violations, s_viol);
-    atomicAdd(&acc->dups, s_dups);
-    atomicAdd(&acc->t_count, s_tcount);
+  {
+    // warp reduce (min / max on u64 via shuffles, counts via __reduce_add_sync), then
+    // lane 0 of each warp issues the global atomics: 8 x 13 atomics per block in total
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      u64 t;
+      t = __shfl_xor_sync(0xffffffffu, a_lo0, m); a_lo0 = t < a_lo0 ? t : a_lo0;
+      t = __shfl_xor_sync(0xffffffffu, a_lo1, m); a_lo1 = t < a_lo1 ? t : a_lo1;
+      t = __shfl_xor_sync(0xffffffffu, a_hi0, m); a_hi0 = t > a_hi0 ? t : a_hi0;
+      t = __shfl_xor_sync(0xffffffffu, a_hi1, m); a_hi1 = t > a_hi1 ? t : a_hi1;
+      t = __shfl_xor_sync(0xffffffffu, a_latest, m); a_latest = t > a_latest ? t : a_latest;
+    }
+    a_nc0 = __reduce_add_sync(0xffffffffu, a_nc0); a_nc1 = __reduce_add_sync(0xffffffffu, a_nc1);
+    a_nr0 = __reduce_add_sync(0xffffffffu, a_nr0); a_nr1 = __reduce_add_sync(0xffffffffu, a_nr1);
+    a_viol = __reduce_add_sync(0xffffffffu, a_viol); a_dups = __reduce_add_sync(0xffffffffu, a_dups);
+    a_tc = __reduce_add_sync(0xffffffffu, a_tc); a_both = __reduce_add_sync(0xffffffffu, a_both);
+    if ((tid & 31) == 0) {
+      if (a_nc0) { atomicMin(&acc->lo[0], a_lo0); atomicMax(&acc->hi[0], a_hi0); atomicAdd(&acc->ncand[0], (u64)a_nc0); }
+      if (a_nc1) { atomicMin(&acc->lo[1], a_lo1); atomicMax(&acc->hi[1], a_hi1); atomicAdd(&acc->ncand[1], (u64)a_nc1); }
+      if (a_nr0) atomicAdd(&acc->nrows[0], (u64)a_nr0);
+      if (a_nr1) atomicAdd(&acc->nrows[1], (u64)a_nr1);
+      atomicMax(&acc->latest_step, a_latest);
+      if (a_viol) atomicAdd(&acc->violations, (u64)a_viol);
+      if (a_dups) atomicAdd(&acc->dups, (u64)a_dups);
+      if (a_tc) atomicAdd(&acc->t_count, (u64)a_tc);
+      if (a_both) atomicAdd(&acc->n_both, (u64)a_both);
+    }
   }
   block_sum<7, WR_THREADS>(sums, partials + (size_t)blockIdx.x * 7);
 }
@@ -1385,6 +1402,7 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
     out->hi[k] = acc.ncand[k] ? acc.hi[k] : 0;
   }
   out->t_count = acc.t_count;
+  out->n_both = acc.n_both;
   c->win_ncand[0] = acc.ncand[0]; c->win_ncand[1] = acc.ncand[1];
   c->win_ready = true;
   (void)rc;

@@ -27,7 +27,7 @@ from . import _abi
 
 KIND_TIME, KIND_MEM = _abi.KIND_TIME, _abi.KIND_MEM
 
-_INFO_LEN = 20
+_INFO_LEN = 21
 _ALIGN_LEN = 15
 
 # analytics/trends/schema.py:27-62
@@ -203,12 +203,13 @@ class WindowReducer:
             "n_cand": [int(w.n_cand[0]), int(w.n_cand[1])],
             "lo": [int(w.lo[0]), int(w.lo[1])], "hi": [int(w.hi[0]), int(w.hi[1])],
             "t_sums": [float(x) for x in w.t_sums], "t_count": int(w.t_count),
+            "n_both": int(getattr(w, "n_both", 0)),
         }
 
     @staticmethod
     def _info_pack(d: Dict[str, Any]) -> List[float]:
         return ([d["n_retained"], d["latest_step"], d["monotone"], d["dup_rows"]]
-                + d["n_rows"] + d["n_cand"] + d["lo"] + d["hi"] + d["t_sums"] + [d["t_count"]])
+                + d["n_rows"] + d["n_cand"] + d["lo"] + d["hi"] + d["t_sums"] + [d["t_count"], d["n_both"]])
 
     @staticmethod
     def _info_unpack(v: Sequence[float]) -> Dict[str, Any]:
@@ -216,7 +217,7 @@ class WindowReducer:
         return {"n_retained": i(v[0]), "latest_step": i(v[1]), "monotone": i(v[2]),
                 "dup_rows": i(v[3]), "n_rows": [i(v[4]), i(v[5])], "n_cand": [i(v[6]), i(v[7])],
                 "lo": [i(v[8]), i(v[9])], "hi": [i(v[10]), i(v[11])],
-                "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19])}
+                "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20])}
 
     def reduce(self, window: int, *, want_series: bool = False) -> ReduceOutput:
         window = max(1, int(window))
@@ -243,10 +244,17 @@ class WindowReducer:
         if ev:
             ev[1].record()
 
-        results = []
-        for kind in (KIND_TIME, KIND_MEM):
-            results.append(self._align(kind, window, infos, ranks, stream))
-        t_res, m_res = results
+        # If on every rank the time and the memory candidates are the very same rows (the
+        # common case: ring not longer than the window, every step has memory), one
+        # alignment serves both sections.
+        merged = all(d["n_cand"][0] == d["n_cand"][1] == d["n_both"] for d in infos.values())
+        t_res = self._align(KIND_TIME, window, infos, ranks, stream)
+        if merged:
+            m_res = KindResult(observed=t_res.observed, used=list(t_res.used), n_common=t_res.n_common,
+                               start_step=t_res.start_step, end_step=t_res.end_step,
+                               windows=dict(t_res.windows))
+        else:
+            m_res = self._align(KIND_MEM, window, infos, ranks, stream)
         if ev:
             ev[2].record()
 

@@ -22,9 +22,20 @@ _ENGINE = None
 _ENGINE_DEVICE: Optional[int] = None
 
 
+_DISABLED = os.environ.get("TRACEML_DISABLED", "0") == "1"
+
+
 def disabled() -> bool:
-    """TRACEML_DISABLED=1 short-circuits every hook (utils/timing.py:28)."""
-    return os.environ.get("TRACEML_DISABLED", "0") == "1"
+    """TRACEML_DISABLED=1 short-circuits every hook.  Read once at import, like the
+    reference's module constants (utils/timing.py:28): the per-region check must not
+    cost an ``os.environ`` lookup."""
+    return _DISABLED
+
+
+def refresh_disabled() -> bool:
+    global _DISABLED
+    _DISABLED = os.environ.get("TRACEML_DISABLED", "0") == "1"
+    return _DISABLED
 
 
 def summary_window_rows() -> int:
@@ -158,5 +169,5 @@ class TraceMLRuntime:
             print(f"[TraceML] final tick failed: {exc}", file=sys.stderr)
 
 
-__all__ = ["TraceMLRuntime", "TraceSessionState", "get_engine", "shutdown_engine", "disabled",
+__all__ = ["TraceMLRuntime", "TraceSessionState", "get_engine", "shutdown_engine", "disabled", "refresh_disabled",
            "get_trace_session_state", "reset_trace_session_state", "summary_window_rows"]
