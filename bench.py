@@ -90,7 +90,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -350,12 +350,14 @@ def main():
                                   ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=R)
 
     # ---- (1) device-resident reduce: K steps, CUDA events, max over ranks
-    for _ in range(args.warmup):
-        res = summ.build(W, 60_000)
+    # (clock sampling starts before the warm-up steps -- same workload -- because the
+    # timed region itself is only a few ms long, shorter than one nvidia-smi period)
     clocks = ClockSampler(local)
-    barrier(world); torch.cuda.synchronize(device)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        res = summ.build(W, 60_000)
+    barrier(world); torch.cuda.synchronize(device)
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {}
@@ -367,7 +369,12 @@ def main():
     e1.record()
     torch.cuda.synchronize(device); barrier(world)
     launches = eng.launch_count - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = None
+    if rank == 0:
+        t_wait = time.time()
+        while not clocks.lines and time.time() - t_wait < 1.5:   # at least one sample under load
+            summ.build(W, 60_000)
+        clk = clocks.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
     ms_step = ms_total / args.steps
     value = b_reduce(R, W) / (ms_step * 1e-3) / 1e9

@@ -251,8 +251,9 @@ int tml_win_select(tml_ctx* ctx, uint32_t kind, uint64_t glo, uint64_t span,
  * valid until the next tml_win_select of the same kind. */
 const void* tml_win_rows(tml_ctx* ctx, uint32_t kind);
 /* CUDA-IPC export / import of that buffer, for the fused NVLink exchange
- * (peer loads inside tml_win_reduce instead of an NCCL all-gather). */
-int tml_win_rows_export(tml_ctx* ctx, uint32_t kind, void* handle64);
+ * (peer loads inside tml_win_reduce instead of an NCCL all-gather).  The handle
+ * names the allocation the rows live in; the rows start byte_offset into it. */
+int tml_win_rows_export(tml_ctx* ctx, uint32_t kind, void* handle64, uint64_t* byte_offset);
 int tml_peer_open(tml_ctx* ctx, const void* handle64, void** peer_ptr);
 int tml_peer_close(tml_ctx* ctx, void* peer_ptr);
 

@@ -141,7 +141,7 @@ SIGNATURES = {
     "tml_win_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
     "tml_win_select": (C.c_int, [vp, u32, u64, u64, vp, u32, vp, C.POINTER(AlignInfo)]),
     "tml_win_rows": (vp, [vp, u32]),
-    "tml_win_rows_export": (C.c_int, [vp, u32, vp]),
+    "tml_win_rows_export": (C.c_int, [vp, u32, vp, C.POINTER(u64)]),
     "tml_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "tml_peer_close": (C.c_int, [vp, vp]),
     "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),

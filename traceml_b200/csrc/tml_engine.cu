@@ -316,36 +316,76 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* out) {
 }
 
 // out[c] = reduce over b of partials[b * ncols + c]; op per column: 0 sum, 1 max.
-__global__ void k_finalize(const double* partials, int nblk, int ncols, u32 max_mask, double* out) {
-  int c = threadIdx.x;
+// One warp per column: lane l folds blocks l, l+32, ... in order, then a fixed
+// shuffle tree -- deterministic for a given grid, and ~nblk/32 dependent loads deep.
+__global__ void k_finalize(const double* __restrict__ partials, int nblk, int ncols, u32 max_mask,
+                           double* __restrict__ out) {
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (c >= ncols) return;
-  bool is_max = (max_mask >> c) & 1u;
+  const bool is_max = (max_mask >> c) & 1u;
   double x = is_max ? -INFINITY : 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     double p = partials[(size_t)b * ncols + c];
     x = is_max ? fmax(x, p) : (x + p);
   }
-  out[c] = x;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    double y = shfl_xor_f64(x, m);
+    x = is_max ? fmax(x, y) : (x + y);
+  }
+  if (lane == 0) out[c] = x;
 }
 
 // ------------------------------------------------------------------ K3a: window rows
-// Persistent grid; each iteration converts a 256-record tile.  The tile is
-// loaded with fully coalesced 16-B loads into XOR-swizzled shared memory so
-// the per-thread 128-B record read is bank-conflict-free, and rows leave
-// through a second swizzled buffer as coalesced 16-B stores.
+// Persistent grid; each iteration converts a 256-record tile (32 KB in, 18.3 KB out).
+//   * the tile is fetched with cp.async (LDGSTS, 16 B per thread per copy, fully
+//     coalesced) into an XOR-swizzled shared buffer; two buffers, so tile i+1 is in
+//     flight while tile i is converted -- the kernel is HBM-latency-bound otherwise
+//     (ncu r01: long-scoreboard stalls, 25 % occupancy);
+//   * the swizzle makes the per-thread 128-B record read bank-conflict-free;
+//   * rows leave through a second swizzled buffer as coalesced 16-B stores;
+//   * integer side results live in registers for the whole persistent loop.
 
 #define WR_THREADS 256
+#define WR_SMEM_BYTES (2 * WR_THREADS * 128 + WR_THREADS * 64 + (WR_THREADS + 2) * 8 + (WR_THREADS + 2) + 64)
 
-__global__ void __launch_bounds__(WR_THREADS) k_window_rows(
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void wr_issue_tile(uint4* buf, const uint4* __restrict__ ring4, u32 ring_slots,
+                                              u64 first_k, u64 n, u64 base, int tid) {
+  // slot of the tile's first record: one 64-bit modulo per tile, then add-and-wrap
+  const u64 slot0 = (first_k + base) % ring_slots;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int idx = c * WR_THREADS + tid;
+    const int r = idx >> 3, q = idx & 7;
+    if (base + (u64)r < n) {
+      u64 slot = slot0 + (u64)r;
+      while (slot >= ring_slots) slot -= ring_slots;
+      cp_async16(&buf[r * 8 + (q ^ (r & 7))], &ring4[slot * 8 + q]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     const tml_step_record* __restrict__ ring, u32 ring_slots, u64 first_k, u64 n, u64 t_start,
     tml_window_row* __restrict__ rows, u64* __restrict__ steps, u8* __restrict__ flags,
     WinAcc* acc, double* partials) {
-  __shared__ uint4 s_in[WR_THREADS * 8];   // 32 KB
-  uint4* const s_out = s_in;               // rows leave through the same buffer (16 KB used)
-  __shared__ u64 s_steps[WR_THREADS + 2];
-  __shared__ u8 s_hasmem[WR_THREADS + 2];
+  extern __shared__ __align__(16) unsigned char wr_smem[];
+  uint4* s_in0 = reinterpret_cast<uint4*>(wr_smem);
+  uint4* s_in1 = s_in0 + WR_THREADS * 8;
+  uint4* s_out = s_in1 + WR_THREADS * 8;
+  u64* s_steps = reinterpret_cast<u64*>(s_out + WR_THREADS * 4);
+  u8* s_hasmem = reinterpret_cast<u8*>(s_steps + (WR_THREADS + 2));
+
   // integer side results: per-thread registers over the persistent loop, one
-  // warp-shuffle + shared-memory reduction per block at the end (no atomics in the loop)
+  // warp-shuffle reduction + a handful of global atomics per warp at the end
   u64 a_lo0 = ~0ull, a_lo1 = ~0ull, a_hi0 = 0, a_hi1 = 0, a_latest = 0;
   u32 a_nc0 = 0, a_nc1 = 0, a_nr0 = 0, a_nr1 = 0, a_viol = 0, a_dups = 0, a_tc = 0, a_both = 0;
   const int tid = threadIdx.x;
@@ -353,20 +393,18 @@ __global__ void __launch_bounds__(WR_THREADS) k_window_rows(
   const u64 ntiles = (n + WR_THREADS - 1) / WR_THREADS;
   const uint4* ring4 = reinterpret_cast<const uint4*>(ring);
 
-  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  u64 tile = blockIdx.x;
+  if (tile < ntiles) wr_issue_tile(s_in0, ring4, ring_slots, first_k, n, tile * WR_THREADS, tid);
+  cp_async_commit();
+
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    uint4* s_in = (it & 1) ? s_in1 : s_in0;
+    uint4* s_nx = (it & 1) ? s_in0 : s_in1;
     const u64 base = tile * WR_THREADS;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      int idx = c * WR_THREADS + tid;
-      int r = idx >> 3, q = idx & 7;
-      u64 i = base + (u64)r;
-      if (i < n) {
-        u64 slot = (first_k + i) % ring_slots;
-        s_in[r * 8 + (q ^ (r & 7))] = __ldg(&ring4[slot * 8 + q]);
-      }
-    }
-    // halo step ids for first/last-of-step tests
+    const u64 next = tile + gridDim.x;
+    if (next < ntiles) wr_issue_tile(s_nx, ring4, ring_slots, first_k, n, next * WR_THREADS, tid);
+    cp_async_commit();
+    // halo step ids for the first/last-of-step tests
     if (tid == 0) {
       if (base > 0) {
         const tml_step_record* p = &ring[(first_k + base - 1) % ring_slots];
@@ -377,32 +415,35 @@ __global__ void __launch_bounds__(WR_THREADS) k_window_rows(
         s_steps[WR_THREADS + 1] = p->step; s_hasmem[WR_THREADS + 1] = (u8)(p->flags & TML_REC_HAS_MEM);
       }
     }
+    cp_async_wait<1>();  // this tile has landed; the next one stays in flight
     __syncthreads();
 
     const u64 i = base + (u64)tid;
     const bool live = i < n;
-    uint4 ch[8];
+    uint4 c0, c1, c2, c3, c5, c6;
     u64 step = 0;
     u32 rflags = 0;
     if (live) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) ch[q] = s_in[tid * 8 + (q ^ (tid & 7))];
-      step = (u64)ch[0].x | ((u64)ch[0].y << 32);
-      rflags = ch[6].w;
+      const int sw = tid & 7;
+      c0 = s_in[tid * 8 + (0 ^ sw)]; c1 = s_in[tid * 8 + (1 ^ sw)];
+      c2 = s_in[tid * 8 + (2 ^ sw)]; c3 = s_in[tid * 8 + (3 ^ sw)];
+      c5 = s_in[tid * 8 + (5 ^ sw)]; c6 = s_in[tid * 8 + (6 ^ sw)];
+      step = (u64)c0.x | ((u64)c0.y << 32);
+      rflags = c6.w;
       s_steps[tid + 1] = step;
       s_hasmem[tid + 1] = (u8)(rflags & TML_REC_HAS_MEM);
     }
     __syncthreads();
 
     if (live) {
-      const u64 d0 = (u64)ch[0].z | ((u64)ch[0].w << 32);
-      const u64 d1 = (u64)ch[1].x | ((u64)ch[1].y << 32);
-      const u64 d2 = (u64)ch[1].z | ((u64)ch[1].w << 32);
-      const u64 d3 = (u64)ch[2].x | ((u64)ch[2].y << 32);
-      const u64 d4 = (u64)ch[2].z | ((u64)ch[2].w << 32);
-      const u64 d5 = (u64)ch[3].x | ((u64)ch[3].y << 32);
-      const u64 pa = (u64)ch[5].x | ((u64)ch[5].y << 32);
-      const u64 pr = (u64)ch[5].z | ((u64)ch[5].w << 32);
+      const u64 d0 = (u64)c0.z | ((u64)c0.w << 32);
+      const u64 d1 = (u64)c1.x | ((u64)c1.y << 32);
+      const u64 d2 = (u64)c1.z | ((u64)c1.w << 32);
+      const u64 d3 = (u64)c2.x | ((u64)c2.y << 32);
+      const u64 d4 = (u64)c2.z | ((u64)c2.w << 32);
+      const u64 d5 = (u64)c3.x | ((u64)c3.y << 32);
+      const u64 pa = (u64)c5.x | ((u64)c5.y << 32);
+      const u64 pr = (u64)c5.z | ((u64)c5.w << 32);
       // ns -> ms: a true IEEE division (not a multiply by 1e-6) so the value is the
       // correctly rounded quotient, identical to Python's ns / 1e6.
       const double dl = __ddiv_rn((double)d0, 1.0e6);
@@ -460,16 +501,17 @@ __global__ void __launch_bounds__(WR_THREADS) k_window_rows(
     uint4* rows4 = reinterpret_cast<uint4*>(rows);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      int idx = c * WR_THREADS + tid;
-      int r = idx >> 2, q = idx & 3;
-      u64 ii = base + (u64)r;
+      const int idx = c * WR_THREADS + tid;
+      const int r = idx >> 2, q = idx & 3;
+      const u64 ii = base + (u64)r;
       if (ii < n) rows4[ii * 4 + q] = s_out[r * 4 + (q ^ ((r >> 1) & 3))];
     }
+    // the next iteration's first __syncthreads orders these reads before s_out is rewritten,
+    // and its prefetch target (this iteration's s_in) was last read before the second sync above
   }
+  cp_async_wait<0>();
   __syncthreads();
   {
-    // warp reduce (min / max on u64 via shuffles, counts via __reduce_add_sync), then
-    // lane 0 of each warp issues the global atomics: 8 x 13 atomics per block in total
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
       u64 t;
@@ -630,14 +672,24 @@ __global__ void __launch_bounds__(SEL_THREADS) k_sel_scatter(
 
 #define GA_THREADS 256
 
+// Are the selected rows one contiguous run of this rank's window rows?  (They are
+// whenever the rank has no holes / duplicates inside the common window.)  Then the
+// aligned rows ARE rows[first .. first+n) and k_gather skips the copy.
+__global__ void k_check_contig(const u32* __restrict__ sel_rows, u64 nsel, u32* __restrict__ noncontig) {
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x + 1; j < nsel; j += (u64)gridDim.x * blockDim.x)
+    if (sel_rows[j] != sel_rows[j - 1] + 1u) *noncontig = 1u;
+}
+
 __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __restrict__ rows,
                                                       const u32* __restrict__ sel_rows, u64 nsel,
                                                       tml_window_row* __restrict__ xrows,
+                                                      const u32* __restrict__ noncontig,
                                                       double* partials /* [grid][16] */) {
   __shared__ double s_part[GA_THREADS / 32][4][4];
   const uint4* rows4 = reinterpret_cast<const uint4*>(rows);
   uint4* x4 = reinterpret_cast<uint4*>(xrows);
   const int q = threadIdx.x & 3;
+  const bool copy = (*noncontig) != 0u;
   double a0 = 0, a1 = 0, a2 = (q == 3) ? -INFINITY : 0.0, a3 = (q == 3) ? -INFINITY : 0.0;
   const u64 nthreads = (u64)gridDim.x * GA_THREADS;
   const u64 work = nsel * 4ull;
@@ -651,7 +703,7 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
     if (ok) {
       const u32 src = sel_rows[j];
       v = __ldg(&rows4[(u64)src * 4 + q]);
-      x4[j * 4 + q] = v;
+      if (copy) x4[j * 4 + q] = v;
     }
     double2 d = *reinterpret_cast<double2*>(&v);
     // q1 -> q2: fwd + bwd ; q0 -> q2: dl
@@ -1037,6 +1089,8 @@ struct tml_ctx {
   u64 cap_x[2] = {0, 0};
   tml_window_row* d_xrows[2] = {nullptr, nullptr};
   u64 n_common[2] = {0, 0};
+  const tml_window_row* rows_ptr[2] = {nullptr, nullptr};  // aligned rows: d_xrows[k] or a slice of d_rows
+  u32* d_noncontig = nullptr;
   u64 cap_sel = 0;
   u32* d_selrow = nullptr;
   u64* d_selstep = nullptr;
@@ -1104,6 +1158,7 @@ int tml_init(int device, int rank, int world, uint32_t ring_slots, uint32_t proc
   CK(cudaHostGetDevicePointer((void**)&c->d_pmirror, c->h_pmirror, 0));
   CK(cudaMalloc(&c->d_winacc, sizeof(WinAcc)));
   CK(cudaMalloc(&c->d_total, sizeof(u64)));
+  CK(cudaMalloc(&c->d_noncontig, sizeof(u32)));
   CK(cudaMalloc(&c->d_partials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
   CK(cudaMalloc(&c->d_final, 64 * sizeof(double)));
   CK(cudaMalloc(&c->d_bandcnt, 64 * sizeof(u64)));
@@ -1122,6 +1177,7 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_rows); cudaFree(c->d_steps); cudaFree(c->d_flags);
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_rowof[k]); cudaFree(c->d_xrows[k]); }
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
+  cudaFree(c->d_noncontig);
   cudaFree(c->d_winacc); cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
   cudaFreeHost(c->h_stage);
   delete c;
@@ -1371,12 +1427,18 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   memset(&init, 0, sizeof(init));
   init.lo[0] = init.lo[1] = ~0ull;
   CK(cudaMemcpyAsync(c->d_winacc, &init, sizeof(init), cudaMemcpyHostToDevice, s));
-  const int grid = grid_for(c, n, WR_THREADS);
-  k_window_rows<<<grid, WR_THREADS, 0, s>>>(c->d_ring, c->ring_slots, first_k, n, c->win_tstart,
+  static bool wr_attr = false;
+  if (!wr_attr) {
+    CK(cudaFuncSetAttribute(k_window_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM_BYTES));
+    wr_attr = true;
+  }
+  int grid = (int)((n + WR_THREADS - 1) / WR_THREADS);
+  if (grid > c->n_sms * 2) grid = c->n_sms * 2;  // 2 resident CTAs per SM (83 KB smem each)
+  k_window_rows<<<grid, WR_THREADS, WR_SMEM_BYTES, s>>>(c->d_ring, c->ring_slots, first_k, n, c->win_tstart,
                                             c->d_rows, c->d_steps, c->d_flags, c->d_winacc,
                                             c->d_partials);
   CK(cudaPeekAtLastError());
-  k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, 7, 0u, c->d_final);
+  k_finalize<<<1, 32 * 7, 0, s>>>(c->d_partials, grid, 7, 0u, c->d_final);
   CK(cudaPeekAtLastError());
   c->launches += 2;
   if (n - c->win_tstart <= TML_EXACT_SUM_MAX) {  // reference-order sums (overwrite the tree sums)
@@ -1441,6 +1503,7 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   CK(cudaSetDevice(c->device));
   memset(out, 0, sizeof(*out));
   c->n_common[kind] = 0;
+  c->rows_ptr[kind] = nullptr;
   if (span == 0 || !presence) return TML_OK;
   const u32 nb = (u32)((span + SEL_TILE - 1) / SEL_TILE);
   int rc = ensure(&c->d_blockcnt, &c->cap_blk, nb);
@@ -1475,9 +1538,14 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   // a rank that has no candidates of its own does not own rows for the window
   if (c->win_n == 0 || c->win_ncand[kind] == 0) return TML_OK;
   const int grid = grid_for(c, keep * 4, GA_THREADS);
-  k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, c->d_selrow, keep, c->d_xrows[kind], c->d_partials);
+  CK(cudaMemsetAsync(c->d_noncontig, 0, sizeof(u32), s));
+  k_check_contig<<<grid_for(c, keep, 256), 256, 0, s>>>(c->d_selrow, keep, c->d_noncontig);
   CK(cudaPeekAtLastError());
-  k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
+  k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, c->d_selrow, keep, c->d_xrows[kind], c->d_noncontig,
+                                       c->d_partials);
+  CK(cudaPeekAtLastError());
+  c->launches += 1;
+  k_finalize<<<1, 32 * 16, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
   CK(cudaPeekAtLastError());
   c->launches += 2;
   const bool exact = (kind == TML_KIND_TIME) && keep <= TML_EXACT_SUM_MAX;
@@ -1490,7 +1558,15 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   CK(cudaMemcpyAsync(st + 64, c->d_final, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 256, c->d_selstep, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 264, c->d_selstep + (keep - 1), sizeof(u64), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 272, c->d_noncontig, sizeof(u32), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 276, c->d_selrow, sizeof(u32), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  {
+    u32 noncontig = 0, first_row = 0;
+    memcpy(&noncontig, st + 272, sizeof(u32));
+    memcpy(&first_row, st + 276, sizeof(u32));
+    c->rows_ptr[kind] = noncontig ? c->d_xrows[kind] : (c->d_rows + first_row);
+  }
   double f[16];
   memcpy(f, st + 64, sizeof(f));
   // partial layout [q][k]: q0 {dl} q1 {fwd,bwd} q2 {opt,cpu,traced,total} q3 {alloc,resv,maxa,maxr}
@@ -1506,15 +1582,20 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
 
 const void* tml_win_rows(tml_ctx* c, uint32_t kind) {
   if (!c || kind > 1) return nullptr;
-  return c->d_xrows[kind];
+  return c->rows_ptr[kind];
 }
 
-int tml_win_rows_export(tml_ctx* c, uint32_t kind, void* handle64) {
-  if (!c || kind > 1 || !handle64) return TML_ERR_ARG;
-  if (!c->d_xrows[kind]) return set_err(TML_ERR_STATE, "no aligned rows to export");
+int tml_win_rows_export(tml_ctx* c, uint32_t kind, void* handle64, uint64_t* byte_offset) {
+  if (!c || kind > 1 || !handle64 || !byte_offset) return TML_ERR_ARG;
+  if (!c->rows_ptr[kind]) return set_err(TML_ERR_STATE, "no aligned rows to export");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle is 64 B");
   CK(cudaSetDevice(c->device));
-  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, c->d_xrows[kind]));
+  // IPC handles name whole allocations: export the base and the slice's offset
+  const char* p = (const char*)c->rows_ptr[kind];
+  const char* base = (p >= (const char*)c->d_rows && p < (const char*)(c->d_rows + c->cap_rows))
+                         ? (const char*)c->d_rows : (const char*)c->d_xrows[kind];
+  CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, (void*)base));
+  *byte_offset = (uint64_t)(p - base);
   return TML_OK;
 }
 
@@ -1628,7 +1709,7 @@ int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* o
   const int grid = grid_for(c, n, PR_THREADS);
   k_proc_reduce<<<grid, PR_THREADS, 0, s>>>(c->d_pring, c->proc_slots, first_k, n, c->d_partials);
   CK(cudaPeekAtLastError());
-  k_finalize<<<1, 32, 0, s>>>(c->d_partials, grid, PR_COLS, PR_MAXMASK, c->d_final);
+  k_finalize<<<1, 32 * PR_COLS, 0, s>>>(c->d_partials, grid, PR_COLS, PR_MAXMASK, c->d_final);
   CK(cudaPeekAtLastError());
   c->launches += 2;
   char* st = (char*)c->h_stage;

@@ -1,0 +1,115 @@
+// tml_step_ext.cpp -- torch-side glue of the STEP PATH (python module traceml_b200._tml_step).
+//
+// Two jobs, both plumbing between PyTorch and the C-ABI of libtraceml_b200.so:
+//
+//  1. Allocator counters.  The reference pays three Python allocator-stat calls per
+//     step (torch.cuda.reset_peak_memory_stats / max_memory_allocated /
+//     max_memory_reserved, src/traceml/utils/step_memory.py:57,73-74), each building
+//     a ~100-entry dict under the allocator mutex.  Here c10's DeviceStats is read
+//     directly and the two integers go straight into tml_step_commit, which hands
+//     them to the commit kernel through the host-mapped counter page.
+//
+//  2. Region open / close without Python-side stream lookups or ctypes marshalling:
+//     begin()/end()/host()/commit() resolve torch's CURRENT stream natively
+//     (c10::cuda::getCurrentCUDAStream) and call the C-ABI entry points, which are
+//     bound once with dlsym -- the boundary stays the C-ABI, this file adds no
+//     telemetry logic of its own.
+#include <c10/cuda/CUDACachingAllocator.h>
+#include <c10/cuda/CUDAStream.h>
+#include <dlfcn.h>
+#include <torch/extension.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+
+namespace {
+
+using begin_fn = int (*)(void*, uint32_t, void*);
+using end_fn = int (*)(void*, uint32_t, int, void*);
+using host_fn = int (*)(void*, uint32_t, uint64_t);
+using commit_fn = int (*)(void*, uint64_t, uint64_t, uint64_t, uint32_t, double, void*);
+
+void* g_ctx = nullptr;
+int g_device = 0;
+begin_fn g_begin = nullptr;
+end_fn g_end = nullptr;
+host_fn g_host = nullptr;
+commit_fn g_commit = nullptr;
+
+void bind(const std::string& lib_path, uint64_t ctx, int64_t device) {
+  void* h = dlopen(lib_path.c_str(), RTLD_NOW | RTLD_GLOBAL);
+  if (!h) throw std::runtime_error(std::string("dlopen failed: ") + dlerror());
+  g_begin = reinterpret_cast<begin_fn>(dlsym(h, "tml_phase_begin"));
+  g_end = reinterpret_cast<end_fn>(dlsym(h, "tml_phase_end"));
+  g_host = reinterpret_cast<host_fn>(dlsym(h, "tml_phase_host"));
+  g_commit = reinterpret_cast<commit_fn>(dlsym(h, "tml_step_commit"));
+  if (!g_begin || !g_end || !g_host || !g_commit)
+    throw std::runtime_error("libtraceml_b200.so lacks a step-path symbol");
+  g_ctx = reinterpret_cast<void*>(ctx);
+  g_device = static_cast<int>(device);
+}
+
+void unbind() { g_ctx = nullptr; }
+
+inline void* cur_stream() {
+  return c10::cuda::getCurrentCUDAStream(static_cast<c10::DeviceIndex>(g_device)).stream();
+}
+
+int64_t begin(int64_t phase) {
+  if (!g_ctx) return -3;
+  return g_begin(g_ctx, static_cast<uint32_t>(phase), cur_stream());
+}
+
+int64_t end(int64_t phase, int64_t slot) {
+  if (!g_ctx) return -3;
+  return g_end(g_ctx, static_cast<uint32_t>(phase), static_cast<int>(slot), cur_stream());
+}
+
+int64_t host(int64_t phase, int64_t dur_ns) {
+  if (!g_ctx) return -3;
+  return g_host(g_ctx, static_cast<uint32_t>(phase), dur_ns < 0 ? 0ull : static_cast<uint64_t>(dur_ns));
+}
+
+// mem_device >= 0: read that device's allocator peaks and flag the record HAS_MEM
+int64_t commit(int64_t step, int64_t mem_device, double host_ts) {
+  if (!g_ctx) return -3;
+  uint64_t a = 0, r = 0;
+  uint32_t flags = 0;
+  if (mem_device >= 0) {
+    const auto st = c10::cuda::CUDACachingAllocator::getDeviceStats(static_cast<c10::DeviceIndex>(mem_device));
+    a = static_cast<uint64_t>(st.allocated_bytes[0].peak);
+    r = static_cast<uint64_t>(st.reserved_bytes[0].peak);
+    flags = 1u;
+  }
+  return g_commit(g_ctx, static_cast<uint64_t>(step), a, r, flags, host_ts, cur_stream());
+}
+
+std::tuple<int64_t, int64_t> peak_bytes(int64_t device) {
+  const auto st = c10::cuda::CUDACachingAllocator::getDeviceStats(static_cast<c10::DeviceIndex>(device));
+  return {st.allocated_bytes[0].peak, st.reserved_bytes[0].peak};
+}
+
+void reset_peaks(int64_t device) {
+  c10::cuda::CUDACachingAllocator::resetPeakStats(static_cast<c10::DeviceIndex>(device));
+}
+
+std::tuple<int64_t, int64_t> current_bytes(int64_t device) {
+  const auto st = c10::cuda::CUDACachingAllocator::getDeviceStats(static_cast<c10::DeviceIndex>(device));
+  return {st.allocated_bytes[0].current, st.reserved_bytes[0].current};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("bind", &bind, "bind the C-ABI step-path entry points and the engine context");
+  m.def("unbind", &unbind);
+  m.def("begin", &begin, "tml_phase_begin on torch's current stream -> slot");
+  m.def("end", &end, "tml_phase_end on torch's current stream");
+  m.def("host", &host, "tml_phase_host");
+  m.def("commit", &commit, "tml_step_commit with the allocator peaks of mem_device (or none if < 0)");
+  m.def("peak_bytes", &peak_bytes, "(peak allocated, peak reserved) bytes of one device");
+  m.def("reset_peaks", &reset_peaks, "reset the allocator's peak counters");
+  m.def("current_bytes", &current_bytes, "(allocated, reserved) bytes right now");
+}

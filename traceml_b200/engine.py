@@ -185,14 +185,17 @@ class Engine:
         return torch.as_tensor(_DevView(ptr, n_common * 8), device=f"cuda:{self.device}")
 
     def win_rows_export(self, kind: int) -> bytes:
+        """72 bytes: the 64-B CUDA-IPC handle of the allocation + the rows' byte offset."""
         buf = C.create_string_buffer(64)
-        _abi.check(self._lib.tml_win_rows_export(self._h, kind, buf), "tml_win_rows_export")
-        return bytes(buf.raw)
+        off = C.c_uint64(0)
+        _abi.check(self._lib.tml_win_rows_export(self._h, kind, buf, C.byref(off)),
+                   "tml_win_rows_export")
+        return bytes(buf.raw) + int(off.value).to_bytes(8, "little")
 
     def peer_open(self, handle: bytes) -> int:
         p = C.c_void_p()
-        _abi.check(self._lib.tml_peer_open(self._h, handle, C.byref(p)), "tml_peer_open")
-        return int(p.value)
+        _abi.check(self._lib.tml_peer_open(self._h, handle[:64], C.byref(p)), "tml_peer_open")
+        return int(p.value) + int.from_bytes(handle[64:72], "little")
 
     def win_reduce(self, rows, mask: int, n_common: int, shard_lo: int,
                    shard_hi: int, series, stream: int = 0) -> None:

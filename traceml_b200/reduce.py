@@ -375,11 +375,11 @@ class WindowReducer:
             blob = b""
             for l in range(self.L):
                 blob += (self.engines[l].win_rows_export(kind) if self._grank(l) in used
-                         else bytes(64))
+                         else bytes(72))
             allh = {}
             for p, b in enumerate(self.comm.all_gather_bytes(blob, dev)):
                 for l in range(self.L):
-                    allh[p * self.L + l] = b[l * 64:(l + 1) * 64]
+                    allh[p * self.L + l] = b[l * 72:(l + 1) * 72]
             e0 = self.engines[0]
             for r in used:
                 if r in my:

@@ -95,6 +95,11 @@ def get_engine(device: Optional[int] = None):
 def shutdown_engine() -> None:
     global _ENGINE, _ENGINE_DEVICE
     with _LOCK:
+        import sys
+
+        timing = sys.modules.get("traceml_b200.utils.timing")
+        if timing is not None:
+            timing._reset()
         if _ENGINE is not None:
             _ENGINE.close()
         _ENGINE = None

@@ -12,21 +12,45 @@ from __future__ import annotations
 import functools
 import os
 import sys
+import time
 from typing import Callable
 
+from ..instrumentation import patches as _patches
+from ..records import PHASE_STEP
 from ..runtime import disabled, get_trace_session_state
+from ..utils import timing as _timing
 from ..utils.flush_buffers import flush_step_events
 from ..utils.step_memory import StepMemoryTracker
 from ..utils.timing import timed_region
+from . import initial as _initial
 
 STEP = "_traceml_internal:step_time"
+_perf_ns = time.perf_counter_ns
+_wall = time.time
+_STATE = get_trace_session_state()
+_INFO_KEY = "_traceml_b200_info"
+_INFO_TTL = 256  # steps between re-checks of the model's device
 
 
 def _auto_optimizer() -> bool:
-    from .initial import get_init_config
-
-    cfg = get_init_config()
+    cfg = _initial._CONFIG
     return cfg is None or cfg.mode == "auto"
+
+
+def _model_info(model):
+    """(mem_device or -1, forward target ids, ttl) cached on the model instance: the
+    device lookup and the DDP/FSDP unwrapping are not redone every step."""
+    info = model.__dict__.get(_INFO_KEY)
+    if info is not None and info[2][0] > 0:
+        info[2][0] -= 1
+        return info
+    tracker = StepMemoryTracker(model)
+    info = (tracker.index if tracker.is_cuda else -1, _patches.forward_targets(model), [_INFO_TTL])
+    try:
+        model.__dict__[_INFO_KEY] = info
+    except Exception:
+        pass
+    return info
 
 
 def _log(message: str, exc: Exception) -> None:
@@ -36,7 +60,7 @@ def _log(message: str, exc: Exception) -> None:
 class trace_step:
     """``with trace_step(model): ...`` -- one training step."""
 
-    __slots__ = ("model", "tracker", "region", "flags", "active")
+    __slots__ = ("model", "tracker", "region", "flags", "active", "t0", "mem_dev", "prev", "fast")
 
     def __init__(self, model):
         self.model = model
@@ -44,11 +68,41 @@ class trace_step:
         self.tracker = None
         self.region = None
         self.flags = None
+        self.fast = None
 
     def __enter__(self):
         if not self.active:
             return self
-        from ..instrumentation import patches
+        patches = _patches
+        fast = _timing._FAST
+        if fast is None and _timing._ENG is None:
+            try:
+                _timing._resolve()
+                fast = _timing._FAST
+            except Exception as exc:
+                _log("engine start failed", exc)
+        if fast is not None:
+            # fast path: same sequence as below with the three context managers and
+            # the tracker object folded into this one (no per-step allocations)
+            self.fast = fast
+            try:
+                info = _model_info(self.model)
+                self.mem_dev = info[0]
+                if info[0] >= 0:
+                    fast.reset_peaks(info[0])
+                t = patches._TLS
+                self.prev = (t.fwd, t.fwd_depth, t.fwd_targets)
+                t.fwd, t.fwd_depth, t.fwd_targets = True, 0, info[1]
+                t.bwd = True
+                t.h2d = True
+                if _auto_optimizer():
+                    patches.ensure_optimizer_timing_installed()
+            except Exception as exc:
+                _log("step setup failed", exc)
+                self.prev = None
+                self.mem_dev = -1
+            self.t0 = _perf_ns()
+            return self
 
         try:
             self.tracker = StepMemoryTracker(self.model)
@@ -68,6 +122,25 @@ class trace_step:
 
     def __exit__(self, exc_type, exc, tb):
         if not self.active:
+            return False
+        fast = self.fast
+        if fast is not None:
+            dur = _perf_ns() - self.t0
+            try:
+                t = _patches._TLS
+                if self.prev is not None:
+                    t.fwd, t.fwd_depth, t.fwd_targets = self.prev
+                t.bwd, t.bwd_depth = False, 0
+                t.h2d = False
+                fast.host(PHASE_STEP, dur)
+                if exc_type is None:
+                    _STATE.advance_step()
+                rc = fast.commit(_STATE.step, self.mem_dev, _wall())
+                if rc < 0:
+                    _timing._ENG.step_discard()
+                    print(f"[TraceML] step {_STATE.step} not committed (status {rc})", file=sys.stderr)
+            except Exception as e:
+                _log("flush failed", e)
             return False
         self.flags.__exit__(exc_type, exc, tb)
         self.region.__exit__(exc_type, exc, tb)

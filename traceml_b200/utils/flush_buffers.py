@@ -20,9 +20,7 @@ def flush_step_events(model, step: int) -> None:
     try:
         from . import timing
 
-        if timing._raw_stream is None:
-            timing._bind_torch()
-        eng = get_engine()
+        eng = timing._ENG or timing._resolve()
         pend = take_pending(model)
         alloc = resv = 0
         flags = 0

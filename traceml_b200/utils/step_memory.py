@@ -23,7 +23,7 @@ def _alloc_ext():
     if not _alloc_tried:
         _alloc_tried = True
         try:
-            from .. import _tml_alloc  # built by __graft_entry__.build()
+            from .. import _tml_step as _tml_alloc  # built by __graft_entry__.build()
 
             _alloc = _tml_alloc
         except Exception as exc:

@@ -31,6 +31,36 @@ _PHASE_BY_NAME = {n: i for i, n in enumerate(PHASE_EVENT_NAMES)}
 _perf_ns = time.perf_counter_ns
 _raw_stream = None  # torch._C._cuda_getCurrentRawStream, bound lazily
 _cur_dev = None
+_ENG = None         # the process engine, resolved on first use
+_FAST = None        # traceml_b200._tml_step bound to that engine (None: ctypes path)
+
+
+def _resolve():
+    """First region of the process: create the engine, bind the native step glue."""
+    global _ENG, _FAST
+    eng = get_engine()
+    if _raw_stream is None:
+        _bind_torch()
+    fast = None
+    try:
+        from .. import _abi, _tml_step
+
+        _tml_step.bind(_abi.LIB_PATH, int(eng._h.value), int(eng.device))
+        fast = _tml_step
+    except Exception as exc:
+        print(f"[TraceML] native step glue unavailable ({exc}); using the ctypes path", file=sys.stderr)
+    _ENG, _FAST = eng, fast
+    return eng
+
+
+def _reset() -> None:
+    global _ENG, _FAST
+    if _FAST is not None:
+        try:
+            _FAST.unbind()
+        except Exception:
+            pass
+    _ENG, _FAST = None, None
 
 
 class TimeScope(str, Enum):
@@ -112,11 +142,13 @@ class timed_region:
         if not self.record:
             return self
         try:
-            eng = self.eng = get_engine()
+            eng = self.eng = _ENG or _resolve()
             if self.gpu:
-                if _raw_stream is None:
-                    _bind_torch()
-                self.slot = eng._begin(eng._h, self.phase, _raw_stream(_cur_dev()))
+                fast = _FAST
+                if fast is not None:
+                    self.slot = fast.begin(self.phase)
+                else:
+                    self.slot = eng._begin(eng._h, self.phase, _raw_stream(_cur_dev()))
                 if self.slot < 0:
                     self.t0 = _perf_ns()  # graph capture / launch failure: host clock
             else:
@@ -130,11 +162,18 @@ class timed_region:
         if not self.record:
             return False
         try:
-            eng = self.eng
-            if self.slot >= 0:
-                eng._end(eng._h, self.phase, self.slot, _raw_stream(_cur_dev()))
+            fast = _FAST
+            if fast is not None:
+                if self.slot >= 0:
+                    fast.end(self.phase, self.slot)
+                else:
+                    fast.host(self.phase, _perf_ns() - self.t0)
             else:
-                eng._host(eng._h, self.phase, _perf_ns() - self.t0)
+                eng = self.eng
+                if self.slot >= 0:
+                    eng._end(eng._h, self.phase, self.slot, _raw_stream(_cur_dev()))
+                else:
+                    eng._host(eng._h, self.phase, _perf_ns() - self.t0)
         except Exception as e:  # nothing here may break training
             print(f"[TraceML] timed_region teardown failed: {e}", file=sys.stderr)
         return False
@@ -149,7 +188,7 @@ def record_event(evt: TimeEvent) -> None:
         return
     try:
         ms = evt.gpu_time_ms if evt.gpu_time_ms is not None else (evt.cpu_end - evt.cpu_start) * 1000.0
-        eng = get_engine()
+        eng = _ENG or _resolve()
         eng._host(eng._h, phase_of(evt.name), max(0, int(round(float(ms) * 1.0e6))))
     except Exception as exc:
         print(f"[TraceML] record_event failed: {exc}", file=sys.stderr)
