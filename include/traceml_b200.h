@@ -206,6 +206,9 @@ typedef struct tml_win_info {
   /* rows that are candidates of BOTH kinds: n_both == n_cand[0] == n_cand[1]
    * means the time and memory candidate sets are the same rows               */
   uint64_t n_both;
+  /* per kind: 1 if every window row is a candidate and their step ids are
+   * consecutive (then tml_win_select_dense applies)                          */
+  uint32_t dense[2];
 } tml_win_info;
 
 /* Stage 1 (local).  Linearises the ring into WindowRows (ns -> ms), step ids
@@ -246,6 +249,14 @@ typedef struct tml_align_info {
 int tml_win_select(tml_ctx* ctx, uint32_t kind, uint64_t glo, uint64_t span,
                    const uint8_t* presence_dev, uint32_t window, void* stream,
                    tml_align_info* out);
+
+/* Stage 2+3 shortcut for the lock-step case: when every participating rank's
+ * window is dense (tml_win_info.dense) the common window is simply the last W
+ * step ids of [max lo, min hi]; no presence map or scan is needed, the aligned
+ * rows are a contiguous slice of the window rows.  Same outputs as
+ * tml_win_select. */
+int tml_win_select_dense(tml_ctx* ctx, uint32_t kind, uint64_t first_step,
+                         uint64_t n_common, void* stream, tml_align_info* out);
 
 /* Device pointer / byte size of this rank's aligned rows (n_common x 64 B),
  * valid until the next tml_win_select of the same kind. */

@@ -27,3 +27,20 @@ for _ in range(reps):
     out = summ.build(W, 60000)
 torch.cuda.synchronize()
 print("ok", out["step_time"]["diagnosis"]["primary"]["status"], out["reduce"].timings_ms)
+
+if os.environ.get("TML_PYPROF"):
+    import cProfile
+    import pstats
+    import time
+
+    t0 = time.perf_counter()
+    for _ in range(20):
+        summ.build(W, 60000)
+    torch.cuda.synchronize()
+    print("wall ms/build", (time.perf_counter() - t0) / 20 * 1e3)
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(20):
+        summ.build(W, 60000)
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(25)

@@ -62,7 +62,7 @@ class FakeEngine:
             n_cand=[int(self.cand[0].sum()), int(self.cand[1].sum())],
             lo=[int(self.steps[self.cand[k]].min()) if self.cand[k].any() else 0 for k in (0, 1)],
             hi=[int(self.steps[self.cand[k]].max()) if self.cand[k].any() else 0 for k in (0, 1)],
-            t_sums=sums, t_count=int(sel.sum()), n_both=int((self.cand[0] & self.cand[1]).sum()))
+            t_sums=sums, t_count=int(sel.sum()), n_both=int((self.cand[0] & self.cand[1]).sum()), dense=(0, 0))
         return out
 
     # ---- stage 2

@@ -50,7 +50,7 @@ class LiveStats(C.Structure):
 class WinInfo(C.Structure):
     _fields_ = [("n_retained", u64), ("latest_step", u64), ("monotone", u32), ("dup_rows", u32),
                 ("n_rows", u64 * 2), ("n_cand", u64 * 2), ("lo", u64 * 2), ("hi", u64 * 2),
-                ("t_sums", f64 * 7), ("t_count", u64), ("n_both", u64)]
+                ("t_sums", f64 * 7), ("t_count", u64), ("n_both", u64), ("dense", u32 * 2)]
 
 
 class AlignInfo(C.Structure):
@@ -140,6 +140,7 @@ SIGNATURES = {
     "tml_win_prepare": (C.c_int, [vp, u32, vp, C.POINTER(WinInfo)]),
     "tml_win_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
     "tml_win_select": (C.c_int, [vp, u32, u64, u64, vp, u32, vp, C.POINTER(AlignInfo)]),
+    "tml_win_select_dense": (C.c_int, [vp, u32, u64, u64, vp, C.POINTER(AlignInfo)]),
     "tml_win_rows": (vp, [vp, u32]),
     "tml_win_rows_export": (C.c_int, [vp, u32, vp, C.POINTER(u64)]),
     "tml_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),

@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
                                                       const u32* __restrict__ sel_rows, u64 nsel,
                                                       tml_window_row* __restrict__ xrows,
                                                       const u32* __restrict__ noncontig,
+                                                      long long dense_first,
                                                       double* partials /* [grid][16] */) {
   __shared__ double s_part[GA_THREADS / 32][4][4];
   const uint4* rows4 = reinterpret_cast<const uint4*>(rows);
@@ -701,8 +702,8 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
     const u64 j = t >> 2;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (ok) {
-      const u32 src = sel_rows[j];
-      v = __ldg(&rows4[(u64)src * 4 + q]);
+      const u64 src = dense_first >= 0 ? (u64)dense_first + j : (u64)sel_rows[j];
+      v = __ldg(&rows4[src * 4 + q]);
       if (copy) x4[j * 4 + q] = v;
     }
     double2 d = *reinterpret_cast<double2*>(&v);
@@ -768,9 +769,18 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
 __global__ void __launch_bounds__(32) k_seq_sums(const tml_window_row* __restrict__ rows,
                                                  const u8* __restrict__ flags, u32 need,
                                                  long long first, long long last, int aligned,
+                                                 const tml_window_row* __restrict__ xrows,
+                                                 const u32* __restrict__ noncontig,
+                                                 const u32* __restrict__ sel_rows,
+                                                 long long dense_first,
                                                  double* __restrict__ out) {
   const int lane = threadIdx.x;
   double acc = 0.0;
+  // aligned mode: the aligned rows are either the gathered copy or a contiguous slice
+  if (aligned) {
+    if (dense_first >= 0) rows = rows + dense_first;
+    else rows = (*noncontig) ? xrows : (rows + sel_rows[0]);
+  }
   const double2* r2 = reinterpret_cast<const double2*>(rows);
 #pragma unroll 4
   for (long long i = last; i >= first; --i) {
@@ -1083,6 +1093,8 @@ struct tml_ctx {
   u8* d_flags = nullptr;
   u64 win_n = 0, win_tstart = 0;
   u64 win_ncand[2] = {0, 0};
+  u64 win_lo[2] = {0, 0}, win_hi[2] = {0, 0};
+  bool win_dense[2] = {false, false};
   bool win_ready = false;
   u64 cap_span[2] = {0, 0};
   u32* d_rowof[2] = {nullptr, nullptr};
@@ -1443,7 +1455,7 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   c->launches += 2;
   if (n - c->win_tstart <= TML_EXACT_SUM_MAX) {  // reference-order sums (overwrite the tree sums)
     k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, c->d_flags, RF_USABLE | RF_IN_TIME, (long long)c->win_tstart,
-                                (long long)n - 1, 0, c->d_final);
+                                (long long)n - 1, 0, nullptr, nullptr, nullptr, -1ll, c->d_final);
     CK(cudaPeekAtLastError());
     c->launches += 1;
   }
@@ -1466,6 +1478,15 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   out->t_count = acc.t_count;
   out->n_both = acc.n_both;
   c->win_ncand[0] = acc.ncand[0]; c->win_ncand[1] = acc.ncand[1];
+  // dense: every window row is a candidate and the candidates' step ids are consecutive, so
+  // row(step) = first_row + (step - lo) and the aligned rows are a contiguous slice
+  const u64 rows_in[2] = {n - c->win_tstart, n};
+  for (int k = 0; k < 2; ++k) {
+    c->win_lo[k] = out->lo[k]; c->win_hi[k] = out->hi[k];
+    c->win_dense[k] = acc.ncand[k] > 0 && acc.ncand[k] == rows_in[k] &&
+                      (out->hi[k] - out->lo[k] + 1) == acc.ncand[k];
+    out->dense[k] = c->win_dense[k] ? 1u : 0u;
+  }
   c->win_ready = true;
   (void)rc;
   if (!out->monotone)
@@ -1542,7 +1563,7 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   k_check_contig<<<grid_for(c, keep, 256), 256, 0, s>>>(c->d_selrow, keep, c->d_noncontig);
   CK(cudaPeekAtLastError());
   k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, c->d_selrow, keep, c->d_xrows[kind], c->d_noncontig,
-                                       c->d_partials);
+                                       -1ll, c->d_partials);
   CK(cudaPeekAtLastError());
   c->launches += 1;
   k_finalize<<<1, 32 * 16, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
@@ -1550,7 +1571,8 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   c->launches += 2;
   const bool exact = (kind == TML_KIND_TIME) && keep <= TML_EXACT_SUM_MAX;
   if (exact) {
-    k_seq_sums<<<1, 32, 0, s>>>(c->d_xrows[kind], nullptr, 0u, 0ll, (long long)keep - 1, 1, c->d_final + 16);
+    k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)keep - 1, 1, c->d_xrows[kind],
+                                c->d_noncontig, c->d_selrow, -1ll, c->d_final + 16);
     CK(cudaPeekAtLastError());
     c->launches += 1;
     CK(cudaMemcpyAsync(st + 320, c->d_final + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1577,6 +1599,53 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   memcpy(&out->start_step, st + 256, sizeof(u64));
   memcpy(&out->end_step, st + 264, sizeof(u64));
   out->n_rows = keep;
+  return TML_OK;
+}
+
+int tml_win_select_dense(tml_ctx* c, uint32_t kind, uint64_t first_step, uint64_t n_common,
+                         void* stream, tml_align_info* out) {
+  if (!c || kind > 1 || !out) return TML_ERR_ARG;
+  if (!c->win_ready) return set_err(TML_ERR_STATE, "tml_win_select_dense before tml_win_prepare");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  c->n_common[kind] = n_common;
+  c->rows_ptr[kind] = nullptr;
+  out->n_common = n_common;
+  if (n_common == 0 || c->win_n == 0 || c->win_ncand[kind] == 0) return TML_OK;
+  if (!c->win_dense[kind] || first_step < c->win_lo[kind] ||
+      first_step + n_common - 1 > c->win_hi[kind])
+    return set_err(TML_ERR_STATE, "window is not dense over the requested steps");
+  const u64 first_row = (kind == TML_KIND_TIME ? c->win_tstart : 0) + (first_step - c->win_lo[kind]);
+  c->rows_ptr[kind] = c->d_rows + first_row;
+  const int grid = grid_for(c, n_common * 4, GA_THREADS);
+  CK(cudaMemsetAsync(c->d_noncontig, 0, sizeof(u32), s));
+  k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, nullptr, n_common, nullptr, c->d_noncontig,
+                                       (long long)first_row, c->d_partials);
+  CK(cudaPeekAtLastError());
+  k_finalize<<<1, 32 * 16, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
+  CK(cudaPeekAtLastError());
+  c->launches += 2;
+  const bool exact = (kind == TML_KIND_TIME) && n_common <= TML_EXACT_SUM_MAX;
+  char* st = (char*)c->h_stage;
+  if (exact) {
+    k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)n_common - 1, 1, nullptr, nullptr,
+                                nullptr, (long long)first_row, c->d_final + 16);
+    CK(cudaPeekAtLastError());
+    c->launches += 1;
+    CK(cudaMemcpyAsync(st + 320, c->d_final + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaMemcpyAsync(st + 64, c->d_final, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  double f[16];
+  memcpy(f, st + 64, sizeof(f));
+  out->t_sums[0] = f[0]; out->t_sums[1] = f[4]; out->t_sums[2] = f[5]; out->t_sums[3] = f[8];
+  out->t_sums[4] = f[9]; out->t_sums[5] = f[10]; out->t_sums[6] = f[11];
+  out->m_sums[0] = f[12]; out->m_sums[1] = f[13]; out->m_sums[2] = f[14]; out->m_sums[3] = f[15];
+  if (exact) memcpy(out->t_sums, st + 320, 7 * sizeof(double));
+  out->start_step = first_step;
+  out->end_step = first_step + n_common - 1;
+  out->n_rows = n_common;
   return TML_OK;
 }
 
@@ -1650,7 +1719,10 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
   p.series = a->series; p.n_common = a->n_common;
   p.shard_lo = a->shard_lo; p.shard_hi = a->shard_hi;
   p.mask = a->mask; p.n_ranks = a->n_ranks;
-  const int grid = grid_for(c, (a->shard_hi - a->shard_lo) * 4, RD_THREADS);
+  // 32 regs x 256 threads: 8 CTAs/SM resident; a multiple of the SM count, grid-stride inside
+  u64 need = ((a->shard_hi - a->shard_lo) * 4 + RD_THREADS - 1) / RD_THREADS;
+  const u64 cap = (u64)c->n_sms * 8ull;
+  const int grid = (int)(need < cap ? (need ? need : 1) : cap);
   switch (a->n_ranks) {
     case 1: launch_reduce<1>(grid, s, p); break;
     case 2: launch_reduce<2>(grid, s, p); break;

@@ -172,6 +172,13 @@ class Engine:
                                             stream, C.byref(out)), "tml_win_select")
         return out
 
+    def win_select_dense(self, kind: int, first_step: int, n_common: int,
+                         stream: int = 0) -> _abi.AlignInfo:
+        out = _abi.AlignInfo()
+        _abi.check(self._lib.tml_win_select_dense(self._h, kind, int(first_step), int(n_common),
+                                                  stream, C.byref(out)), "tml_win_select_dense")
+        return out
+
     def win_rows_ptr(self, kind: int) -> int:
         return int(self._lib.tml_win_rows(self._h, kind) or 0)
 

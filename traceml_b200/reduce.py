@@ -27,7 +27,7 @@ from . import _abi
 
 KIND_TIME, KIND_MEM = _abi.KIND_TIME, _abi.KIND_MEM
 
-_INFO_LEN = 21
+_INFO_LEN = 23
 _ALIGN_LEN = 15
 
 # analytics/trends/schema.py:27-62
@@ -204,12 +204,13 @@ class WindowReducer:
             "lo": [int(w.lo[0]), int(w.lo[1])], "hi": [int(w.hi[0]), int(w.hi[1])],
             "t_sums": [float(x) for x in w.t_sums], "t_count": int(w.t_count),
             "n_both": int(getattr(w, "n_both", 0)),
+            "dense": [int(x) for x in getattr(w, "dense", (0, 0))],
         }
 
     @staticmethod
     def _info_pack(d: Dict[str, Any]) -> List[float]:
         return ([d["n_retained"], d["latest_step"], d["monotone"], d["dup_rows"]]
-                + d["n_rows"] + d["n_cand"] + d["lo"] + d["hi"] + d["t_sums"] + [d["t_count"], d["n_both"]])
+                + d["n_rows"] + d["n_cand"] + d["lo"] + d["hi"] + d["t_sums"] + [d["t_count"], d["n_both"]] + d["dense"])
 
     @staticmethod
     def _info_unpack(v: Sequence[float]) -> Dict[str, Any]:
@@ -217,7 +218,7 @@ class WindowReducer:
         return {"n_retained": i(v[0]), "latest_step": i(v[1]), "monotone": i(v[2]),
                 "dup_rows": i(v[3]), "n_rows": [i(v[4]), i(v[5])], "n_cand": [i(v[6]), i(v[7])],
                 "lo": [i(v[8]), i(v[9])], "hi": [i(v[10]), i(v[11])],
-                "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20])}
+                "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20]), "dense": [i(v[21]), i(v[22])]}
 
     def reduce(self, window: int, *, want_series: bool = False) -> ReduceOutput:
         window = max(1, int(window))
@@ -303,17 +304,30 @@ class WindowReducer:
             return res
         span = ghi - glo + 1
         dev = self.device
+        if all(infos[r]["dense"][kind] for r in part):
+            # lock-step fast path: every participant holds every step id of [glo, ghi]
+            n_common = min(span, window)
+            first = ghi - n_common + 1
+            flat: List[float] = []
+            for l, e in enumerate(self.engines):
+                a = e.win_select_dense(kind, first, n_common, stream)
+                flat.extend([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
+                            + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
+            return self._collect_aligns(kind, res, flat, part, infos)
         presence = None
         for l, e in enumerate(self.engines):
             p = torch.empty(span, dtype=torch.uint8, device=dev)
             e.win_presence(kind, glo, span, p, stream)
             presence = p if presence is None else torch.minimum(presence, p)
         self.comm.all_reduce_min_(presence)
-        flat: List[float] = []
+        flat = []
         for l, e in enumerate(self.engines):
             a = e.win_select(kind, glo, span, presence, window, stream)
             flat.extend([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
                         + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
+        return self._collect_aligns(kind, res, flat, part, infos)
+
+    def _collect_aligns(self, kind, res, flat, part, infos) -> KindResult:
         gathered = []
         for row in self.comm.all_gather_vec(flat, self.device):
             lst = []
