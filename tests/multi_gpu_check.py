@@ -1,0 +1,82 @@
+"""Multi-GPU parity check, launched by torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multi_gpu_check.py
+
+Every rank loads ITS replay records, the job runs the cross-rank reduce with the
+fused NVLink peer-load exchange ("p2p") and with the NCCL all-gather exchange
+("nccl"); rank 0 checks both against the oracle (test infrastructure)."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from helpers import assert_struct, oracle_mem_rows, oracle_proc_rows, oracle_time_rows, plain, strip_device
+    from oracle import process_oracle, step_memory_oracle, step_time_oracle
+    from traceml_b200 import replay, sections
+    from traceml_b200.engine import Engine
+    from traceml_b200.reduce import TorchDistComm
+
+    failures = 0
+    for scenario, S, W in (("straggler", 700, 10_000), ("ragged", 900, 256), ("input_straggler", 200_000, 150_000)):
+        recs_all = replay.make_step_replay(scenario, world, S, seed=11) if S <= 1000 else None
+        mine = (recs_all[rank] if recs_all is not None else
+                replay.make_step_replay(scenario, world, S, seed=11, only_ranks=[rank])[rank])
+        procs = replay.make_proc_replay("overhang", world, 500, seed=11, only_ranks=[rank])[rank]
+        results = {}
+        for mode in ("p2p", "nccl"):
+            eng = Engine(device=local, rank=rank, world=world, ring_slots=max(64, len(mine) + 8), proc_slots=1024)
+            if len(mine):
+                eng.load_steps(mine)
+            eng.load_procs(procs)
+            torch.cuda.synchronize()
+            res = sections.SummaryEngine([eng], TorchDistComm(), exchange=mode,
+                                         ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world).build(W, W)
+            assert res["reduce"].exchange == mode
+            results[mode] = res
+            dist.barrier()
+            eng.close()
+        if rank == 0:
+            try:
+                a, b = results["p2p"], results["nccl"]
+                assert_struct(plain(a["step_time"]), plain(b["step_time"]), f"{scenario}: p2p == nccl", rel=0.0)
+                assert_struct(plain(a["step_memory"]["diagnosis"]), plain(b["step_memory"]["diagnosis"]), "mem p2p == nccl", rel=0.0)
+                if recs_all is not None:
+                    ref = step_time_oracle.step_time_section(oracle_time_rows(recs_all, W), max_rows=W)
+                    g = a["step_time"]
+                    assert_struct(plain(g["data"]), plain({k: ref["data"][k] for k in g["data"]}), "data")
+                    assert_struct(plain(g["diagnosis"]), plain(ref["diagnosis"]), "diagnosis")
+                    mref = step_memory_oracle.step_memory_section(
+                        oracle_mem_rows(recs_all), window_size=W, gpu_total_bytes=a["step_memory"]["gpu_total_bytes"])
+                    assert_struct(strip_device(plain(a["step_memory"]["diagnosis"]))["primary"],
+                                  strip_device(plain(mref["diagnosis"]))["primary"], "mem.primary")
+                    procs_all = replay.make_proc_replay("overhang", world, 500, seed=11)
+                    pref = process_oracle.process_section(oracle_proc_rows(procs_all, world), max_rows=W)
+                    assert_struct(plain(a["process"]["primary"]), plain(pref["diagnosis"]["primary"]), "proc.primary")
+                else:
+                    assert a["step_time"]["diagnosis"]["primary"]["kind"] == "INPUT_STRAGGLER"
+                    assert a["step_time"]["data"]["aligned_window"]["steps_analyzed"] == W
+                print(f"[multi_gpu_check] {scenario} R={world} W={W}: OK "
+                      f"({a['step_time']['diagnosis']['primary']['status'] if a['step_time']['diagnosis'] else None}); "
+                      f"p2p {a['reduce'].timings_ms.get('total', 0):.3f} ms, nccl {b['reduce'].timings_ms.get('total', 0):.3f} ms")
+            except AssertionError as exc:
+                failures += 1
+                print(f"[multi_gpu_check] {scenario}: FAILED {exc}")
+    t = torch.tensor([failures], device="cuda")
+    dist.broadcast(t, 0)
+    dist.destroy_process_group()
+    sys.exit(1 if int(t.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
