@@ -234,6 +234,29 @@ def step_overhead(device, world, local, quick=False):
             "empty_lambda": cost(lambda: None),
         }
         eng.drain()
+        # sustained telemetry rate: commit + drain (step records) and 1 kHz-style process samples
+        side = torch.cuda.Stream(device=device)
+        n_rec, got, t0 = 50_000, 0, time.perf_counter()
+        for i in range(n_rec):
+            eng._host(h, 5, 1000)
+            eng._commit(h, i + 1, 0, 0, 0, 0.0, sp)
+            if i % 2048 == 2047:
+                got += len(eng.drain()[0])
+        torch.cuda.synchronize(device)
+        got += len(eng.drain()[0])
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        pgot = 0
+        for i in range(n_rec):
+            eng.proc_commit(i + 1, 0.0, 50.0, 1 << 30, 1 << 30, 1 << 31, 1 << 37, 3, 64, side.cuda_stream)
+            if i % 4096 == 4095:
+                pgot += len(eng.proc_drain()[0])
+        torch.cuda.synchronize(device)
+        pgot += len(eng.proc_drain()[0])
+        dt2 = time.perf_counter() - t1
+        out["telemetry_rate"] = {"step_records_per_s": n_rec / dt, "step_records_drained": got,
+                                 "proc_samples_per_s": n_rec / dt2, "proc_samples_drained": pgot,
+                                 "records": n_rec}
     except Exception as exc:
         out["api_cost_us"] = {"error": str(exc)}
 

@@ -326,6 +326,9 @@ typedef struct tml_proc_agg {
   double max_ratio;    /* MAX(resv / used) over rows with used > 0, else -1  */
   uint32_t max_cores;
   uint32_t any_gpu_available; /* 0/1, valid if n > 0                         */
+  double sum_cpu_lo;   /* low word of the double-double cpu sum: the exact sum
+                          is sum_cpu + sum_cpu_lo (matches SQLite's compensated
+                          AVG to the last bit)                               */
 } tml_proc_agg;
 
 /* Per-rank process aggregates over the last max_rows proc records.  Replaces

@@ -108,7 +108,10 @@ def _agg_from_records(recs, max_rows):
     has = (r["flags"] & 2) != 0
     a.n_gpu = int(has.sum())
     a.ts_min, a.ts_max = float(r["ts"].min()), float(r["ts"].max())
-    a.sum_cpu, a.max_cpu = float(r["cpu_pct"].sum()), float(r["cpu_pct"].max())
+    import math
+
+    a.sum_cpu, a.max_cpu = math.fsum(r["cpu_pct"].tolist()), float(r["cpu_pct"].max())
+    a.sum_cpu_lo = 0.0
     rss = r["rss"].astype(np.float64)
     a.sum_rss, a.max_rss = float(rss.sum()), float(rss.max())
     if a.n_gpu:

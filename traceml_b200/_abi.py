@@ -78,7 +78,7 @@ class ProcAgg(C.Structure):
                 ("sum_cpu", f64), ("max_cpu", f64), ("sum_rss", f64), ("max_rss", f64),
                 ("sum_used", f64), ("max_used", f64), ("sum_resv", f64), ("max_resv", f64),
                 ("max_total", f64), ("max_ratio", f64), ("max_cores", u32),
-                ("any_gpu_available", u32)]
+                ("any_gpu_available", u32), ("sum_cpu_lo", f64)]
 
 
 class RankMeans(C.Structure):

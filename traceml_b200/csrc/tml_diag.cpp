@@ -805,7 +805,12 @@ extern "C" int tml_diag_process(const tml_proc_diag_in* in, char* json_out, size
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return in->ranks[a] < in->ranks[b]; });
   // pooled aggregates (loader.py:56-139): AVG = sum / count over all rows of all ranks
   uint64_t n_all = 0, n_gpu_all = 0;
-  double s_cpu = 0, s_rss = 0, s_used = 0, s_resv = 0;
+  double s_cpu = 0, s_cpu_lo = 0, s_rss = 0, s_used = 0, s_resv = 0;
+  auto dd_add = [](double& hi, double& lo, double xh, double xl) {  // TwoSum accumulate
+    const double s = hi + xh, bp = s - hi;
+    const double err = (hi - (s - bp)) + (xh - bp);
+    hi = s; lo = (lo + xl) + err;
+  };
   double mx_cpu = -INFINITY, mx_rss = -INFINITY, mx_used = -INFINITY, mx_resv = -INFINITY;
   double mx_total = -INFINITY, mx_ramtot = -INFINITY, ts_min = INFINITY, ts_max = -INFINITY;
   int mx_cores = -1, mx_gpucount = -1, any_avail = -1, distinct = 0;
@@ -815,7 +820,7 @@ extern "C" int tml_diag_process(const tml_proc_diag_in* in, char* json_out, size
     ++distinct;
     RankAgg r;
     r.rank = in->ranks[oi]; r.n = a.n; r.has_gpu = a.n_gpu > 0;
-    r.cpu_avg = a.sum_cpu / (double)a.n; r.cpu_peak = a.max_cpu;
+    r.cpu_avg = (a.sum_cpu + a.sum_cpu_lo) / (double)a.n; r.cpu_peak = a.max_cpu;
     r.ram_avg = a.sum_rss / (double)a.n; r.ram_peak = a.max_rss; r.ram_total = in->ram_total[oi];
     r.used_avg = r.has_gpu ? a.sum_used / (double)a.n_gpu : 0; r.used_peak = a.max_used;
     r.resv_avg = r.has_gpu ? a.sum_resv / (double)a.n_gpu : 0; r.resv_peak = a.max_resv;
@@ -824,7 +829,8 @@ extern "C" int tml_diag_process(const tml_proc_diag_in* in, char* json_out, size
     r.gpu_count = r.gpu_available ? in->gpu_count[oi] : 0;
     rs.push_back(r);
     n_all += a.n; n_gpu_all += a.n_gpu;
-    s_cpu += a.sum_cpu; s_rss += a.sum_rss; s_used += a.sum_used; s_resv += a.sum_resv;
+    dd_add(s_cpu, s_cpu_lo, a.sum_cpu, a.sum_cpu_lo);
+    s_rss += a.sum_rss; s_used += a.sum_used; s_resv += a.sum_resv;
     mx_cpu = std::max(mx_cpu, a.max_cpu); mx_rss = std::max(mx_rss, a.max_rss);
     if (r.has_gpu) {
       mx_used = std::max(mx_used, a.max_used); mx_resv = std::max(mx_resv, a.max_resv);
@@ -836,7 +842,7 @@ extern "C" int tml_diag_process(const tml_proc_diag_in* in, char* json_out, size
     any_avail = std::max(any_avail, r.gpu_available ? 1 : 0);
   }
   const bool have = n_all > 0, have_gpu = n_gpu_all > 0;
-  const double cpu_avg = have ? s_cpu / (double)n_all : 0;
+  const double cpu_avg = have ? (s_cpu + s_cpu_lo) / (double)n_all : 0;
   const double ram_avg = have ? s_rss / (double)n_all : 0;
   const double used_avg = have_gpu ? s_used / (double)n_gpu_all : 0;
   const double resv_avg = have_gpu ? s_resv / (double)n_gpu_all : 0;

@@ -987,10 +987,23 @@ __global__ void __launch_bounds__(256) k_bands(const __grid_constant__ BandParam
 // ------------------------------------------------------------------ K6: proc reduce
 // columns: 0 sum_cpu 1 sum_rss 2 sum_used 3 sum_resv | max: 4 cpu 5 rss 6 used 7 resv
 // 8 total 9 ratio 10 ts_max 11 -ts_min 12 cores 13 gpu_available | 14 n_gpu (sum)
+// 15 sum_cpu low word: cpu% is the one non-integer column, and the reference's AVG is
+// SQLite's compensated (Kahan-Babuska) sum, i.e. correctly rounded in practice.  The
+// cpu sum is therefore carried as an unevaluated double-double (hi, lo) through every
+// level of the reduction (TwoSum), so it rounds to the same double and rank-level
+// tie-breaks on cpu_percent agree with the reference.
 
 #define PR_THREADS 256
-#define PR_COLS 15
+#define PR_COLS 16
 #define PR_MAXMASK (((1u << 14) - 1u) & ~0xFu)
+
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double xh, double xl) {
+  const double s = hi + xh;
+  const double bp = s - hi;
+  const double err = (hi - (s - bp)) + (xh - bp);
+  hi = s;
+  lo = (lo + xl) + err;
+}
 
 __global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_record* __restrict__ ring,
                                                            u32 slots, u64 first_k, u64 n,
@@ -1009,7 +1022,7 @@ __global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_recor
     const double resv = (double)((u64)c2.z | ((u64)c2.w << 32));
     const double total = (double)((u64)c3.x | ((u64)c3.y << 32));
     const u32 fl = c3.z, cores = c3.w;
-    a[0] += cpu; a[4] = fmax(a[4], cpu);
+    dd_add(a[0], a[15], cpu, 0.0); a[4] = fmax(a[4], cpu);
     a[1] += rss; a[5] = fmax(a[5], rss);
     a[10] = fmax(a[10], ts); a[11] = fmax(a[11], -ts);
     a[12] = fmax(a[12], (double)cores);
@@ -1024,7 +1037,12 @@ __global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_recor
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < PR_COLS; ++k) {
+  for (int m = 16; m >= 1; m >>= 1) {  // the double-double cpu sum
+    const double oh = shfl_xor_f64(a[0], m), ol = shfl_xor_f64(a[15], m);
+    dd_add(a[0], a[15], oh, ol);
+  }
+#pragma unroll
+  for (int k = 1; k < PR_COLS - 1; ++k) {
     const bool mx = (PR_MAXMASK >> k) & 1u;
     double x = a[k];
 #pragma unroll
@@ -1032,10 +1050,19 @@ __global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_recor
       double y = shfl_xor_f64(x, m);
       x = mx ? fmax(x, y) : (x + y);
     }
-    if (lane == 0) s_part[warp][k] = x;
+    a[k] = x;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < PR_COLS; ++k) s_part[warp][k] = a[k];
   }
   __syncthreads();
-  if (threadIdx.x < PR_COLS) {
+  if (threadIdx.x == 0) {
+    double h = 0.0, l = 0.0;
+    for (int w = 0; w < PR_THREADS / 32; ++w) dd_add(h, l, s_part[w][0], s_part[w][15]);
+    partials[(size_t)blockIdx.x * PR_COLS + 0] = h;
+    partials[(size_t)blockIdx.x * PR_COLS + 15] = l;
+  } else if (threadIdx.x < PR_COLS - 1) {
     const bool mx = (PR_MAXMASK >> threadIdx.x) & 1u;
     double x = mx ? -INFINITY : 0.0;
     for (int w = 0; w < PR_THREADS / 32; ++w) {
@@ -1044,6 +1071,16 @@ __global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_recor
     }
     partials[(size_t)blockIdx.x * PR_COLS + threadIdx.x] = x;
   }
+}
+
+// fold the per-CTA (hi, lo) cpu sums in CTA order with TwoSum -> out[0], out[15]
+__global__ void k_finalize_dd(const double* __restrict__ partials, int nblk, int ncols, int hi_col,
+                              int lo_col, double* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double h = 0.0, l = 0.0;
+  for (int b = 0; b < nblk; ++b) dd_add(h, l, partials[(size_t)b * ncols + hi_col], partials[(size_t)b * ncols + lo_col]);
+  out[hi_col] = h;
+  out[lo_col] = l;
 }
 
 // =================================================================== host side
@@ -1783,7 +1820,9 @@ int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* o
   CK(cudaPeekAtLastError());
   k_finalize<<<1, 32 * PR_COLS, 0, s>>>(c->d_partials, grid, PR_COLS, PR_MAXMASK, c->d_final);
   CK(cudaPeekAtLastError());
-  c->launches += 2;
+  k_finalize_dd<<<1, 32, 0, s>>>(c->d_partials, grid, PR_COLS, 0, 15, c->d_final);
+  CK(cudaPeekAtLastError());
+  c->launches += 3;
   char* st = (char*)c->h_stage;
   CK(cudaMemcpyAsync(st, c->d_final, PR_COLS * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -1791,7 +1830,7 @@ int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* o
   memcpy(f, st, sizeof(f));
   out->n = n;
   out->n_gpu = (u64)f[14];
-  out->sum_cpu = f[0]; out->max_cpu = f[4];
+  out->sum_cpu = f[0]; out->sum_cpu_lo = f[15]; out->max_cpu = f[4];
   out->sum_rss = f[1]; out->max_rss = f[5];
   out->sum_used = f[2]; out->max_used = out->n_gpu ? f[6] : 0.0;
   out->sum_resv = f[3]; out->max_resv = out->n_gpu ? f[7] : 0.0;

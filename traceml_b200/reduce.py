@@ -28,7 +28,10 @@ from . import _abi
 KIND_TIME, KIND_MEM = _abi.KIND_TIME, _abi.KIND_MEM
 
 _INFO_LEN = 23
-_ALIGN_LEN = 15
+_ALIGN_LEN = 15 + 72  # sums + the 72-byte CUDA-IPC rows handle, one byte per double
+_PROC_FIELDS = tuple(f for f, _ in _abi.ProcAgg._fields_)
+_PROC_INT_FIELDS = ("n", "n_gpu", "max_cores", "any_gpu_available")
+_PROC_LEN = len(_PROC_FIELDS)
 
 # analytics/trends/schema.py:27-62
 _BANDS = ((0.15, 0.25), (0.45, 0.55), (0.90, 1.00))
@@ -175,6 +178,7 @@ class ReduceOutput:
     exchange: str
     fused_pass: bool
     timings_ms: Dict[str, float] = field(default_factory=dict)
+    proc_aggs: Dict[int, Dict[str, Any]] = field(default_factory=dict)
 
 
 # ----------------------------------------------------------------------------- reducer
@@ -220,7 +224,8 @@ class WindowReducer:
                 "lo": [i(v[8]), i(v[9])], "hi": [i(v[10]), i(v[11])],
                 "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20]), "dense": [i(v[21]), i(v[22])]}
 
-    def reduce(self, window: int, *, want_series: bool = False) -> ReduceOutput:
+    def reduce(self, window: int, *, want_series: bool = False,
+               proc_rows: Optional[int] = None) -> ReduceOutput:
         window = max(1, int(window))
         dev = self.device
         stream = _stream_of(dev)
@@ -234,13 +239,28 @@ class WindowReducer:
 
         # ---- stage 1: local windows + bounds
         local_infos = [self._info_dict(e.win_prepare(window, stream)) for e in self.engines]
+        k3a_ev = None
+        if ev:
+            k3a_ev = torch.cuda.Event(enable_timing=True)
+            k3a_ev.record()
+        per = _INFO_LEN + (_PROC_LEN if proc_rows else 0)
         flat: List[float] = []
-        for d in local_infos:
+        for l, d in enumerate(local_infos):
             flat.extend(self._info_pack(d))
+            if proc_rows:  # process aggregates (K6) ride in the same exchange
+                a = self.engines[l].proc_reduce(max(1, int(proc_rows)), stream)
+                flat.extend(float(getattr(a, f)) for f in _PROC_FIELDS)
         infos: Dict[int, Dict[str, Any]] = {}
+        proc_aggs: Dict[int, Dict[str, Any]] = {}
         for p, row in enumerate(self.comm.all_gather_vec(flat, dev)):
             for l in range(self.L):
-                infos[p * self.L + l] = self._info_unpack(row[l * _INFO_LEN:(l + 1) * _INFO_LEN])
+                v = row[l * per:(l + 1) * per]
+                infos[p * self.L + l] = self._info_unpack(v[:_INFO_LEN])
+                if proc_rows:
+                    pa = dict(zip(_PROC_FIELDS, v[_INFO_LEN:]))
+                    for f in _PROC_INT_FIELDS:
+                        pa[f] = int(round(pa[f]))
+                    proc_aggs[p * self.L + l] = pa
         ranks = sorted(infos)
         if ev:
             ev[1].record()
@@ -284,12 +304,12 @@ class WindowReducer:
             for i, nm in enumerate(names):
                 timings[nm] = float(ev[i].elapsed_time(ev[i + 1]))
             timings["total"] = float(ev[0].elapsed_time(ev[4]))
-            timings["k3a"] = timings["prepare"]
+            timings["k3a"] = float(ev[0].elapsed_time(k3a_ev))
             timings["k4"] = float(sum(a.elapsed_time(b) for a, b in self._k4_events))
         if not want_series:
             pass
         return ReduceOutput(window=window, ranks=ranks, infos=infos, time=t_res, mem=m_res,
-                            exchange=mode, fused_pass=same, timings_ms=timings)
+                            exchange=mode, fused_pass=same, timings_ms=timings, proc_aggs=proc_aggs)
 
     # ------------------------------------------------------------------ alignment
     def _align(self, kind: int, window: int, infos, ranks, stream) -> KindResult:
@@ -311,8 +331,7 @@ class WindowReducer:
             flat: List[float] = []
             for l, e in enumerate(self.engines):
                 a = e.win_select_dense(kind, first, n_common, stream)
-                flat.extend([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
-                            + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
+                flat.extend(self._align_pack(e, kind, a))
             return self._collect_aligns(kind, res, flat, part, infos)
         presence = None
         for l, e in enumerate(self.engines):
@@ -323,11 +342,21 @@ class WindowReducer:
         flat = []
         for l, e in enumerate(self.engines):
             a = e.win_select(kind, glo, span, presence, window, stream)
-            flat.extend([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
-                        + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
+            flat.extend(self._align_pack(e, kind, a))
         return self._collect_aligns(kind, res, flat, part, infos)
 
+    def _align_pack(self, engine, kind, a) -> List[float]:
+        """15 numbers + (p2p only) the rows' CUDA-IPC handle, so the peer mapping
+        needs no collective of its own."""
+        handle = bytes(72)
+        if self._exchange_mode() == "p2p" and int(a.n_rows) > 0:
+            handle = engine.win_rows_export(kind)
+        return ([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
+                + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums]
+                + [float(b) for b in handle])
+
     def _collect_aligns(self, kind, res, flat, part, infos) -> KindResult:
+        res.handles = {}
         gathered = []
         for row in self.comm.all_gather_vec(flat, self.device):
             lst = []
@@ -335,7 +364,8 @@ class WindowReducer:
                 v = row[l * _ALIGN_LEN:(l + 1) * _ALIGN_LEN]
                 lst.append({"n_common": int(round(v[0])), "start": int(round(v[1])),
                             "end": int(round(v[2])), "n_rows": int(round(v[3])),
-                            "t_sums": list(v[4:11]), "m_sums": list(v[11:15])})
+                            "t_sums": list(v[4:11]), "m_sums": list(v[11:15]),
+                            "handle": bytes(int(round(b)) for b in v[15:87])})
             gathered.append(lst)
         n_common = max(a["n_common"] for lst in gathered for a in lst)
         res.n_common = n_common
@@ -347,6 +377,7 @@ class WindowReducer:
                 if r in part and a["n_rows"] > 0:
                     res.windows[r] = RankWindow(rank=r, n_rows=a["n_rows"], t_sums=a["t_sums"],
                                                 m_sums=a["m_sums"], info=infos[r])
+                    res.handles[r] = a["handle"]
                     res.start_step, res.end_step = a["start"], a["end"]
         res.used = sorted(res.windows)
         return res
@@ -385,22 +416,19 @@ class WindowReducer:
             for r in used:
                 rows[r] = gathered[r * n * 8:(r + 1) * n * 8]
             self._keep = gathered
-        else:  # p2p: CUDA-IPC peer mappings, loads fused into the reduce kernel
-            blob = b""
-            for l in range(self.L):
-                blob += (self.engines[l].win_rows_export(kind) if self._grank(l) in used
-                         else bytes(72))
-            allh = {}
-            for p, b in enumerate(self.comm.all_gather_bytes(blob, dev)):
-                for l in range(self.L):
-                    allh[p * self.L + l] = b[l * 72:(l + 1) * 72]
+        else:
+            # p2p: CUDA-IPC peer mappings, loads fused into the reduce kernel.  No barrier is
+            # needed around it: (1) a rank's rows are complete before it enters the aligns
+            # all-gather (win_select* synchronises its stream), so once that collective
+            # returns every peer's rows are readable; (2) a rank overwrites its rows only in
+            # the NEXT reduce's win_prepare, which comes after this reduce's band all-gather,
+            # and every rank enters that only after its own K4 has finished (win_bands syncs).
             e0 = self.engines[0]
             for r in used:
                 if r in my:
                     rows[r] = self.engines[r - self.comm.index * self.L].win_rows_tensor(kind, n)
                 else:
-                    rows[r] = e0.peer_open(allh[r])
-            self.comm.barrier()  # every rank's rows are complete before peers read them
+                    rows[r] = e0.peer_open(res.handles[r])
         # step-sharded: shard s of W_total shards -> engine with global rank s
         W = self.comm.world * self.L
         lo_first, hi_last = None, None
@@ -422,10 +450,6 @@ class WindowReducer:
             self._k4_events.append((k0, k1))
         res.series = series.view(_abi.TML_SERIES_PER_STEP, n)
         res.shard = (lo_first or 0, hi_last or 0)
-        if mode == "p2p":
-            if self.device.type == "cuda":
-                torch.cuda.current_stream(self.device).synchronize()
-            self.comm.barrier()  # nobody frees / rewrites rows while a peer still reads
 
     # ------------------------------------------------------------------ bands
     def _bands(self, t_res: KindResult, m_res: KindResult, same: bool, stream) -> None:

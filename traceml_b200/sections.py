@@ -284,18 +284,16 @@ class SummaryEngine:
     def build(self, window: int = 10_000, proc_rows: int = 10_000) -> Dict[str, Any]:
         import torch
 
-        out = self.reducer.reduce(window)
-        stream = _stream_of(self.reducer.device)
         gpu_count = self.gpu_count if self.gpu_count is not None else torch.cuda.device_count()
-        local = []
-        for e in self.engines:
-            local.append(proc_agg_dict(e.proc_reduce(max(1, int(proc_rows)), stream),
-                                       ram_total=self.ram_total, gpu_count=gpu_count))
+        out = self.reducer.reduce(window, proc_rows=max(1, int(proc_rows)))
         aggs: Dict[int, Dict[str, Any]] = {}
-        L = len(self.engines)
-        for p, lst in enumerate(self.comm.all_gather_obj(local)):
-            for l, a in enumerate(lst):
-                aggs[p * L + l] = a
+        for r, a in out.proc_aggs.items():
+            d = dict(a)
+            # ram_total / gpu_count are per-host constants (psutil.virtual_memory().total,
+            # torch.cuda.device_count()); single-node scope: identical on every rank
+            d["ram_total"] = float(self.ram_total)
+            d["gpu_count"] = int(gpu_count)
+            aggs[r] = d
         with_gpu = [a for a in aggs.values() if a["n_gpu"] > 0]
         gpu_total = max((a["max_total"] for a in with_gpu), default=None)
         saw = [a for a in aggs.values() if a["n"] > 0]
