@@ -349,6 +349,19 @@ __global__ void k_finalize(const double* __restrict__ partials, int nblk, int nc
 #define WR_THREADS 256
 #define WR_SMEM_BYTES (2 * WR_THREADS * 128 + WR_THREADS * 64 + (WR_THREADS + 2) * 8 + (WR_THREADS + 2) + 64)
 
+// ns -> ms as the CORRECTLY ROUNDED quotient ns / 1e6 (what Python's ns / 1e6 gives)
+// without a division: y = RN(1/1e6), q = RN(a*y), r = a - 1e6*q (exact, FMA),
+// result = RN(q + r*y) -- Markstein's final division step, exact because y is the
+// correctly rounded reciprocal.  tests/test_ns_to_ms_cpu.py checks 10^7+ values against
+// true division on the CPU (2*10^9 were checked once, 0 mismatches).
+__device__ __forceinline__ double ns_to_ms(u64 ns) {
+  const double a = (double)ns;
+  const double y = 1.0e-6;
+  const double q = __dmul_rn(a, y);
+  const double r = __fma_rn(-1.0e6, q, a);
+  return __fma_rn(r, y, q);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -389,7 +402,8 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
   u64 a_lo0 = ~0ull, a_lo1 = ~0ull, a_hi0 = 0, a_hi1 = 0, a_latest = 0;
   u32 a_nc0 = 0, a_nc1 = 0, a_nr0 = 0, a_nr1 = 0, a_viol = 0, a_dups = 0, a_tc = 0, a_both = 0;
   const int tid = threadIdx.x;
-  double sums[7] = {0, 0, 0, 0, 0, 0, 0};
+  double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 7 time sums + sum alloc, sum resv (window rows)
+  double mx_a = -INFINITY, mx_r = -INFINITY;      // rank peaks over the window rows
   const u64 ntiles = (n + WR_THREADS - 1) / WR_THREADS;
   const uint4* ring4 = reinterpret_cast<const uint4*>(ring);
 
@@ -444,14 +458,8 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       const u64 d5 = (u64)c3.x | ((u64)c3.y << 32);
       const u64 pa = (u64)c5.x | ((u64)c5.y << 32);
       const u64 pr = (u64)c5.z | ((u64)c5.w << 32);
-      // ns -> ms: a true IEEE division (not a multiply by 1e-6) so the value is the
-      // correctly rounded quotient, identical to Python's ns / 1e6.
-      const double dl = __ddiv_rn((double)d0, 1.0e6);
-      const double h2d = __ddiv_rn((double)d1, 1.0e6);
-      const double fwd = __ddiv_rn((double)d2, 1.0e6);
-      const double bwd = __ddiv_rn((double)d3, 1.0e6);
-      const double opt = __ddiv_rn((double)d4, 1.0e6);
-      const double wall = __ddiv_rn((double)d5, 1.0e6);
+      const double dl = ns_to_ms(d0), h2d = ns_to_ms(d1), fwd = ns_to_ms(d2);
+      const double bwd = ns_to_ms(d3), opt = ns_to_ms(d4), wall = ns_to_ms(d5);
       const bool has_mem = (rflags & TML_REC_HAS_MEM) != 0u;
       const bool usable = (dl > 0.0) || (fwd > 0.0) || (bwd > 0.0) || (opt > 0.0) || (wall > 0.0);
       const bool in_time = i >= t_start;
@@ -486,6 +494,10 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
         sums[0] += dl; sums[1] += fwd; sums[2] += bwd; sums[3] += opt;
         sums[4] += wall; sums[5] += traced; sums[6] += dl + traced;
         ++a_tc;
+      }
+      if (in_time) {
+        sums[7] += (double)pa; sums[8] += (double)pr;
+        mx_a = fmax(mx_a, (double)pa); mx_r = fmax(mx_r, (double)pr);
       }
 
       // row -> swizzled staging (4 x 16 B)
@@ -537,7 +549,26 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       if (a_both) atomicAdd(&acc->n_both, (u64)a_both);
     }
   }
-  block_sum<7, WR_THREADS>(sums, partials + (size_t)blockIdx.x * 7);
+  block_sum<9, WR_THREADS>(sums, partials + (size_t)blockIdx.x * 11);
+  {  // the two maxima: warp shuffle + shared memory, written as partial columns 9, 10
+    __shared__ double s_mx[WR_THREADS / 32][2];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      mx_a = fmax(mx_a, shfl_xor_f64(mx_a, m));
+      mx_r = fmax(mx_r, shfl_xor_f64(mx_r, m));
+    }
+    if ((tid & 31) == 0) { s_mx[tid >> 5][0] = mx_a; s_mx[tid >> 5][1] = mx_r; }
+    __syncthreads();
+    if (tid < 2) {
+      double x = -INFINITY;
+      for (int w = 0; w < WR_THREADS / 32; ++w) x = fmax(x, s_mx[w][tid]);
+      partials[(size_t)blockIdx.x * 11 + 9 + tid] = x;
+    }
+  }
+}
+
+__global__ void k_copy7(const double* __restrict__ src, double* __restrict__ dst) {
+  if (threadIdx.x < 7) dst[threadIdx.x] = src[threadIdx.x];
 }
 
 // ------------------------------------------------------------------ K3b: presence
@@ -1131,6 +1162,7 @@ struct tml_ctx {
   u64 win_n = 0, win_tstart = 0;
   u64 win_ncand[2] = {0, 0};
   u64 win_lo[2] = {0, 0}, win_hi[2] = {0, 0};
+  double win_tsums[7] = {0}, win_msums[4] = {0};  // sums over the whole time window (K3a)
   bool win_dense[2] = {false, false};
   bool win_ready = false;
   u64 cap_span[2] = {0, 0};
@@ -1487,7 +1519,9 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
                                             c->d_rows, c->d_steps, c->d_flags, c->d_winacc,
                                             c->d_partials);
   CK(cudaPeekAtLastError());
-  k_finalize<<<1, 32 * 7, 0, s>>>(c->d_partials, grid, 7, 0u, c->d_final);
+  k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
+  CK(cudaPeekAtLastError());
+  k_copy7<<<1, 32, 0, s>>>(c->d_final + 32, c->d_final);
   CK(cudaPeekAtLastError());
   c->launches += 2;
   if (n - c->win_tstart <= TML_EXACT_SUM_MAX) {  // reference-order sums (overwrite the tree sums)
@@ -1499,10 +1533,13 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   char* st = (char*)c->h_stage;
   CK(cudaMemcpyAsync(st, c->d_winacc, sizeof(WinAcc), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 256, c->d_final, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 320, c->d_final + 32 + 7, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   WinAcc acc;
   memcpy(&acc, st, sizeof(acc));
   memcpy(out->t_sums, st + 256, 7 * sizeof(double));
+  memcpy(c->win_msums, st + 320, 4 * sizeof(double));
+  memcpy(c->win_tsums, out->t_sums, 7 * sizeof(double));
   out->latest_step = acc.latest_step;
   out->monotone = acc.violations == 0 ? 1u : 0u;
   out->dup_rows = (u32)acc.dups;
@@ -1655,6 +1692,18 @@ int tml_win_select_dense(tml_ctx* c, uint32_t kind, uint64_t first_step, uint64_
     return set_err(TML_ERR_STATE, "window is not dense over the requested steps");
   const u64 first_row = (kind == TML_KIND_TIME ? c->win_tstart : 0) + (first_step - c->win_lo[kind]);
   c->rows_ptr[kind] = c->d_rows + first_row;
+  if (kind == TML_KIND_TIME && first_step == c->win_lo[kind] && n_common == c->win_ncand[kind]) {
+    // the common window IS this rank's whole time window (ranks in lock step): the sums
+    // k_window_rows already produced are the aligned sums -- nothing left to launch.
+    // (aligned step_cpu = sum of traced: alignment.py:72 -> t_sums[4] := t_sums[5])
+    memcpy(out->t_sums, c->win_tsums, sizeof(c->win_tsums));
+    out->t_sums[4] = c->win_tsums[5];
+    memcpy(out->m_sums, c->win_msums, sizeof(c->win_msums));
+    out->start_step = first_step;
+    out->end_step = first_step + n_common - 1;
+    out->n_rows = n_common;
+    return TML_OK;
+  }
   const int grid = grid_for(c, n_common * 4, GA_THREADS);
   CK(cudaMemsetAsync(c->d_noncontig, 0, sizeof(u32), s));
   k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, nullptr, n_common, nullptr, c->d_noncontig,

@@ -31,6 +31,12 @@ class _Flags(threading.local):
     bwd = False
     bwd_depth = 0
     h2d = False
+    # per-thread reusable region objects: the openers below are depth-guarded (forward,
+    # backward) or strictly sequential (h2d), so one object per site is enough and the
+    # per-call allocation disappears
+    r_fwd = None
+    r_bwd = None
+    r_h2d = None
 
 
 _TLS = _Flags()
@@ -55,7 +61,10 @@ def _module_call(self, *args, **kwargs):
         return _ORIG_MODULE_CALL(self, *args, **kwargs)
     t.fwd_depth += 1
     try:
-        with timed_region(FWD, "step", True):
+        region = t.r_fwd
+        if region is None:
+            region = t.r_fwd = timed_region(FWD, "step", True)
+        with region:
             return _ORIG_MODULE_CALL(self, *args, **kwargs)
     finally:
         t.fwd_depth -= 1
@@ -88,7 +97,10 @@ def _tensor_backward(self, *args, **kwargs):
         return _ORIG_TENSOR_BACKWARD(self, *args, **kwargs)
     t.bwd_depth += 1
     try:
-        with timed_region(BWD, "step", True):
+        region = t.r_bwd
+        if region is None:
+            region = t.r_bwd = timed_region(BWD, "step", True)
+        with region:
             return _ORIG_TENSOR_BACKWARD(self, *args, **kwargs)
     finally:
         t.bwd_depth -= 1
@@ -100,7 +112,10 @@ def _autograd_backward(*args, **kwargs):
         return _ORIG_AUTOGRAD_BACKWARD(*args, **kwargs)
     t.bwd_depth += 1
     try:
-        with timed_region(BWD, "step", True):
+        region = t.r_bwd
+        if region is None:
+            region = t.r_bwd = timed_region(BWD, "step", True)
+        with region:
             return _ORIG_AUTOGRAD_BACKWARD(*args, **kwargs)
     finally:
         t.bwd_depth -= 1
@@ -116,9 +131,13 @@ def patch_backward() -> None:
 
 # ----------------------------------------------------------------- h2d
 def _tensor_to(self, *args, **kwargs):
-    if not _TLS.h2d or not should_time_h2d(self, args, kwargs):
+    t = _TLS
+    if not t.h2d or not should_time_h2d(self, args, kwargs):
         return _ORIG_TENSOR_TO(self, *args, **kwargs)
-    with timed_region(H2D, "step", True):
+    region = t.r_h2d
+    if region is None:
+        region = t.r_h2d = timed_region(H2D, "step", True)
+    with region:
         return _ORIG_TENSOR_TO(self, *args, **kwargs)
 
 
