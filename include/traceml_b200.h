@@ -335,6 +335,10 @@ typedef struct tml_proc_agg {
  * the SQL aggregates of reporting/sections/process/loader.py:56-230. */
 int tml_proc_reduce(tml_ctx* ctx, uint32_t max_rows, void* stream,
                     tml_proc_agg* out);
+/* Split form: launch without synchronising; collect after any later
+ * synchronisation of the same stream (tml_win_prepare provides one). */
+int tml_proc_reduce_launch(tml_ctx* ctx, uint32_t max_rows, void* stream);
+int tml_proc_reduce_collect(tml_ctx* ctx, tml_proc_agg* out);
 
 /* ---------------------------------------------------------------- DIAGNOSIS
  * Host C++ rule engines (O(R) scalars).  Each writes one UTF-8 JSON object

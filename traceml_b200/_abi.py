@@ -148,6 +148,8 @@ SIGNATURES = {
     "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),
     "tml_win_bands": (C.c_int, [vp, vp, C.POINTER(BandArgs), vp, C.POINTER(BandOut)]),
     "tml_proc_reduce": (C.c_int, [vp, u32, vp, C.POINTER(ProcAgg)]),
+    "tml_proc_reduce_launch": (C.c_int, [vp, u32, vp]),
+    "tml_proc_reduce_collect": (C.c_int, [vp, C.POINTER(ProcAgg)]),
     "tml_diag_step_time": (C.c_int, [C.POINTER(StDiagIn), C.c_char_p, C.c_size_t]),
     "tml_diag_step_memory": (C.c_int, [C.POINTER(MemDiagIn), C.c_char_p, C.c_size_t]),
     "tml_diag_process": (C.c_int, [C.POINTER(ProcDiagIn), C.c_char_p, C.c_size_t]),

@@ -337,23 +337,19 @@ __global__ void k_finalize(const double* __restrict__ partials, int nblk, int nc
 }
 
 // ------------------------------------------------------------------ K3a: window rows
-// Persistent grid; each iteration converts a 256-record tile (32 KB in, 18.3 KB out).
-//   * the tile is fetched with cp.async (LDGSTS, 16 B per thread per copy, fully
-//     coalesced) into an XOR-swizzled shared buffer; two buffers, so tile i+1 is in
-//     flight while tile i is converted -- the kernel is HBM-latency-bound otherwise
-//     (ncu r01: long-scoreboard stalls, 25 % occupancy);
-//   * the swizzle makes the per-thread 128-B record read bank-conflict-free;
-//   * rows leave through a second swizzled buffer as coalesced 16-B stores;
+// Ring (128-B AoS records) -> WindowRow[] (64 B), step ids, row flags, bounds, sums.
+//   * tiles are fetched with cp.async (LDGSTS, 16 B per lane per copy, fully coalesced)
+//     into XOR-swizzled shared buffers, two per warp, so tile i+1 is in flight while
+//     tile i is converted -- the kernel was HBM-latency-bound before (ncu r01 v1:
+//     long-scoreboard stalls, 25 % occupancy, 1.97 TB/s);
+//   * the swizzle makes the per-lane 128-B record read bank-conflict-free;
+//   * rows leave through a swizzled staging buffer as coalesced 16-B stores;
 //   * integer side results live in registers for the whole persistent loop.
-
-#define WR_THREADS 256
-#define WR_SMEM_BYTES (2 * WR_THREADS * 128 + WR_THREADS * 64 + (WR_THREADS + 2) * 8 + (WR_THREADS + 2) + 64)
 
 // ns -> ms as the CORRECTLY ROUNDED quotient ns / 1e6 (what Python's ns / 1e6 gives)
 // without a division: y = RN(1/1e6), q = RN(a*y), r = a - 1e6*q (exact, FMA),
 // result = RN(q + r*y) -- Markstein's final division step, exact because y is the
-// correctly rounded reciprocal.  tests/test_ns_to_ms_cpu.py checks 10^7+ values against
-// true division on the CPU (2*10^9 were checked once, 0 mismatches).
+// correctly rounded reciprocal (tests/test_ns_to_ms_cpu.py; 2*10^9 values checked once).
 __device__ __forceinline__ double ns_to_ms(u64 ns) {
   const double a = (double)ns;
   const double y = 1.0e-6;
@@ -361,6 +357,12 @@ __device__ __forceinline__ double ns_to_ms(u64 ns) {
   const double r = __fma_rn(-1.0e6, q, a);
   return __fma_rn(r, y, q);
 }
+
+#define WR_THREADS 256
+#define WR_WARPS (WR_THREADS / 32)
+// per warp: two 32-record input buffers (2 x 4 KB) + one 32-row output buffer (2 KB)
+#define WR_WARP_U4 (2 * 32 * 8 + 32 * 4)
+#define WR_SMEM_BYTES (WR_WARPS * WR_WARP_U4 * 16)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -370,13 +372,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void wr_issue_tile(uint4* buf, const uint4* __restrict__ ring4, u32 ring_slots,
-                                              u64 first_k, u64 n, u64 base, int tid) {
-  // slot of the tile's first record: one 64-bit modulo per tile, then add-and-wrap
-  const u64 slot0 = (first_k + base) % ring_slots;
+// one warp fetches its 32-record tile: 8 x cp.async per lane, each instruction = 512 B contiguous
+__device__ __forceinline__ void wr_issue_warp(uint4* buf, const uint4* __restrict__ ring4, u32 ring_slots,
+                                              u64 first_k, u64 n, u64 base, int lane) {
+  const u64 slot0 = (first_k + base) % ring_slots;  // one 64-bit modulo per tile, then add-and-wrap
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const int idx = c * WR_THREADS + tid;
+    const int idx = c * 32 + lane;
     const int r = idx >> 3, q = idx & 7;
     if (base + (u64)r < n) {
       u64 slot = slot0 + (u64)r;
@@ -386,68 +388,66 @@ __device__ __forceinline__ void wr_issue_tile(uint4* buf, const uint4* __restric
   }
 }
 
+// K3a.  Persistent grid, WARP-PRIVATE software pipelines: every warp streams its own
+// 32-record tiles (cp.async double buffer -> XOR-swizzled smem -> registers -> swizzled
+// smem -> coalesced 16-B stores) and synchronises only with __syncwarp; neighbour step
+// ids come from warp shuffles (tile edges: two 8-B global reads).  No block barrier in
+// the loop (ncu r01 v2 showed barrier + wait stalls dominating once the loads were
+// asynchronous).
 __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     const tml_step_record* __restrict__ ring, u32 ring_slots, u64 first_k, u64 n, u64 t_start,
     tml_window_row* __restrict__ rows, u64* __restrict__ steps, u8* __restrict__ flags,
     WinAcc* acc, double* partials) {
   extern __shared__ __align__(16) unsigned char wr_smem[];
-  uint4* s_in0 = reinterpret_cast<uint4*>(wr_smem);
-  uint4* s_in1 = s_in0 + WR_THREADS * 8;
-  uint4* s_out = s_in1 + WR_THREADS * 8;
-  u64* s_steps = reinterpret_cast<u64*>(s_out + WR_THREADS * 4);
-  u8* s_hasmem = reinterpret_cast<u8*>(s_steps + (WR_THREADS + 2));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint4* w_in0 = reinterpret_cast<uint4*>(wr_smem) + warp * WR_WARP_U4;
+  uint4* w_in1 = w_in0 + 32 * 8;
+  uint4* w_out = w_in1 + 32 * 8;
 
-  // integer side results: per-thread registers over the persistent loop, one
-  // warp-shuffle reduction + a handful of global atomics per warp at the end
   u64 a_lo0 = ~0ull, a_lo1 = ~0ull, a_hi0 = 0, a_hi1 = 0, a_latest = 0;
   u32 a_nc0 = 0, a_nc1 = 0, a_nr0 = 0, a_nr1 = 0, a_viol = 0, a_dups = 0, a_tc = 0, a_both = 0;
-  const int tid = threadIdx.x;
   double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 7 time sums + sum alloc, sum resv (window rows)
   double mx_a = -INFINITY, mx_r = -INFINITY;      // rank peaks over the window rows
-  const u64 ntiles = (n + WR_THREADS - 1) / WR_THREADS;
+  const u64 nwt = (n + 31) / 32;
+  const u64 wstride = (u64)gridDim.x * WR_WARPS;
   const uint4* ring4 = reinterpret_cast<const uint4*>(ring);
+  uint4* rows4 = reinterpret_cast<uint4*>(rows);
 
-  u64 tile = blockIdx.x;
-  if (tile < ntiles) wr_issue_tile(s_in0, ring4, ring_slots, first_k, n, tile * WR_THREADS, tid);
+  u64 wt = (u64)blockIdx.x * WR_WARPS + warp;
+  if (wt < nwt) wr_issue_warp(w_in0, ring4, ring_slots, first_k, n, wt * 32, lane);
   cp_async_commit();
 
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    uint4* s_in = (it & 1) ? s_in1 : s_in0;
-    uint4* s_nx = (it & 1) ? s_in0 : s_in1;
-    const u64 base = tile * WR_THREADS;
-    const u64 next = tile + gridDim.x;
-    if (next < ntiles) wr_issue_tile(s_nx, ring4, ring_slots, first_k, n, next * WR_THREADS, tid);
+  for (int it = 0; wt < nwt; wt += wstride, ++it) {
+    uint4* cur = (it & 1) ? w_in1 : w_in0;
+    uint4* nxt = (it & 1) ? w_in0 : w_in1;
+    const u64 base = wt * 32;
+    const u64 next = wt + wstride;
+    if (next < nwt) wr_issue_warp(nxt, ring4, ring_slots, first_k, n, next * 32, lane);
     cp_async_commit();
-    // halo step ids for the first/last-of-step tests
-    if (tid == 0) {
-      if (base > 0) {
-        const tml_step_record* p = &ring[(first_k + base - 1) % ring_slots];
-        s_steps[0] = p->step; s_hasmem[0] = (u8)(p->flags & TML_REC_HAS_MEM);
-      }
-      if (base + WR_THREADS < n) {
-        const tml_step_record* p = &ring[(first_k + base + WR_THREADS) % ring_slots];
-        s_steps[WR_THREADS + 1] = p->step; s_hasmem[WR_THREADS + 1] = (u8)(p->flags & TML_REC_HAS_MEM);
-      }
+    // tile-edge neighbours (first/last-of-step tests) straight from the ring
+    u64 halo_step = 0;
+    u32 halo_flags = 0;
+    if (lane == 0 && base > 0) halo_step = ring[(first_k + base - 1) % ring_slots].step;
+    if (lane == 31 && base + 32 < n) {
+      const tml_step_record* p = &ring[(first_k + base + 32) % ring_slots];
+      halo_step = p->step; halo_flags = p->flags;
     }
     cp_async_wait<1>();  // this tile has landed; the next one stays in flight
-    __syncthreads();
+    __syncwarp();
 
-    const u64 i = base + (u64)tid;
+    const u64 i = base + (u64)lane;
     const bool live = i < n;
-    uint4 c0, c1, c2, c3, c5, c6;
-    u64 step = 0;
-    u32 rflags = 0;
-    if (live) {
-      const int sw = tid & 7;
-      c0 = s_in[tid * 8 + (0 ^ sw)]; c1 = s_in[tid * 8 + (1 ^ sw)];
-      c2 = s_in[tid * 8 + (2 ^ sw)]; c3 = s_in[tid * 8 + (3 ^ sw)];
-      c5 = s_in[tid * 8 + (5 ^ sw)]; c6 = s_in[tid * 8 + (6 ^ sw)];
-      step = (u64)c0.x | ((u64)c0.y << 32);
-      rflags = c6.w;
-      s_steps[tid + 1] = step;
-      s_hasmem[tid + 1] = (u8)(rflags & TML_REC_HAS_MEM);
-    }
-    __syncthreads();
+    const int sw = lane & 7;
+    const uint4 c0 = cur[lane * 8 + (0 ^ sw)], c1 = cur[lane * 8 + (1 ^ sw)];
+    const uint4 c2 = cur[lane * 8 + (2 ^ sw)], c3 = cur[lane * 8 + (3 ^ sw)];
+    const uint4 c5 = cur[lane * 8 + (5 ^ sw)], c6 = cur[lane * 8 + (6 ^ sw)];
+    const u64 step = (u64)c0.x | ((u64)c0.y << 32);
+    const u32 rflags = c6.w;
+    u64 prev_step = __shfl_up_sync(0xffffffffu, step, 1);
+    u64 next_step = __shfl_down_sync(0xffffffffu, step, 1);
+    u32 next_flags = __shfl_down_sync(0xffffffffu, rflags, 1);
+    if (lane == 0) prev_step = halo_step;
+    if (lane == 31) { next_step = halo_step; next_flags = halo_flags; }
 
     if (live) {
       const u64 d0 = (u64)c0.z | ((u64)c0.w << 32);
@@ -464,10 +464,8 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       const bool usable = (dl > 0.0) || (fwd > 0.0) || (bwd > 0.0) || (opt > 0.0) || (wall > 0.0);
       const bool in_time = i >= t_start;
       const bool has_prev = i > 0, has_next = (i + 1) < n;
-      const u64 prev_step = s_steps[tid];
-      const u64 next_step = s_steps[tid + 2];
       const bool first_in_win = (i == t_start) || !has_prev || (prev_step != step);
-      const bool last_m = !has_next || (next_step != step) || (s_hasmem[tid + 2] == 0);
+      const bool last_m = !has_next || (next_step != step) || ((next_flags & TML_REC_HAS_MEM) == 0u);
       u8 f = 0;
       if (usable) f |= RF_USABLE;
       if (has_mem) f |= RF_HAS_MEM;
@@ -503,26 +501,23 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       // row -> swizzled staging (4 x 16 B)
       double2 o0 = make_double2(dl, h2d), o1 = make_double2(fwd, bwd);
       double2 o2 = make_double2(opt, wall), o3 = make_double2((double)pa, (double)pr);
-      const int sw = (tid >> 1) & 3;
-      s_out[tid * 4 + (0 ^ sw)] = *reinterpret_cast<uint4*>(&o0);
-      s_out[tid * 4 + (1 ^ sw)] = *reinterpret_cast<uint4*>(&o1);
-      s_out[tid * 4 + (2 ^ sw)] = *reinterpret_cast<uint4*>(&o2);
-      s_out[tid * 4 + (3 ^ sw)] = *reinterpret_cast<uint4*>(&o3);
+      const int so = (lane >> 1) & 3;
+      w_out[lane * 4 + (0 ^ so)] = *reinterpret_cast<uint4*>(&o0);
+      w_out[lane * 4 + (1 ^ so)] = *reinterpret_cast<uint4*>(&o1);
+      w_out[lane * 4 + (2 ^ so)] = *reinterpret_cast<uint4*>(&o2);
+      w_out[lane * 4 + (3 ^ so)] = *reinterpret_cast<uint4*>(&o3);
     }
-    __syncthreads();
-    uint4* rows4 = reinterpret_cast<uint4*>(rows);
+    __syncwarp();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int idx = c * WR_THREADS + tid;
+      const int idx = c * 32 + lane;
       const int r = idx >> 2, q = idx & 3;
       const u64 ii = base + (u64)r;
-      if (ii < n) rows4[ii * 4 + q] = s_out[r * 4 + (q ^ ((r >> 1) & 3))];
+      if (ii < n) rows4[ii * 4 + q] = w_out[r * 4 + (q ^ ((r >> 1) & 3))];
     }
-    // the next iteration's first __syncthreads orders these reads before s_out is rewritten,
-    // and its prefetch target (this iteration's s_in) was last read before the second sync above
+    __syncwarp();  // w_out and `cur` are free again
   }
   cp_async_wait<0>();
-  __syncthreads();
   {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
@@ -537,7 +532,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     a_nr0 = __reduce_add_sync(0xffffffffu, a_nr0); a_nr1 = __reduce_add_sync(0xffffffffu, a_nr1);
     a_viol = __reduce_add_sync(0xffffffffu, a_viol); a_dups = __reduce_add_sync(0xffffffffu, a_dups);
     a_tc = __reduce_add_sync(0xffffffffu, a_tc); a_both = __reduce_add_sync(0xffffffffu, a_both);
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
       if (a_nc0) { atomicMin(&acc->lo[0], a_lo0); atomicMax(&acc->hi[0], a_hi0); atomicAdd(&acc->ncand[0], (u64)a_nc0); }
       if (a_nc1) { atomicMin(&acc->lo[1], a_lo1); atomicMax(&acc->hi[1], a_hi1); atomicAdd(&acc->ncand[1], (u64)a_nc1); }
       if (a_nr0) atomicAdd(&acc->nrows[0], (u64)a_nr0);
@@ -549,6 +544,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       if (a_both) atomicAdd(&acc->n_both, (u64)a_both);
     }
   }
+  __syncthreads();
   block_sum<9, WR_THREADS>(sums, partials + (size_t)blockIdx.x * 11);
   {  // the two maxima: warp shuffle + shared memory, written as partial columns 9, 10
     __shared__ double s_mx[WR_THREADS / 32][2];
@@ -557,7 +553,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       mx_a = fmax(mx_a, shfl_xor_f64(mx_a, m));
       mx_r = fmax(mx_r, shfl_xor_f64(mx_r, m));
     }
-    if ((tid & 31) == 0) { s_mx[tid >> 5][0] = mx_a; s_mx[tid >> 5][1] = mx_r; }
+    if (lane == 0) { s_mx[warp][0] = mx_a; s_mx[warp][1] = mx_r; }
     __syncthreads();
     if (tid < 2) {
       double x = -INFINITY;
@@ -1179,6 +1175,10 @@ struct tml_ctx {
   u32* d_blockcnt = nullptr;
   u64* d_total = nullptr;
   WinAcc* d_winacc = nullptr;
+  double* d_ppartials = nullptr; // proc reduce partials (own buffers: it overlaps the window reduce)
+  double* d_pfinal = nullptr;
+  bool proc_pending = false;
+  u64 proc_pending_n = 0;
   double* d_partials = nullptr;  // max(grid) * 16 doubles
   double* d_final = nullptr;     // 64 doubles
   u64* d_bandcnt = nullptr;
@@ -1242,6 +1242,8 @@ int tml_init(int device, int rank, int world, uint32_t ring_slots, uint32_t proc
   CK(cudaMalloc(&c->d_noncontig, sizeof(u32)));
   CK(cudaMalloc(&c->d_partials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
   CK(cudaMalloc(&c->d_final, 64 * sizeof(double)));
+  CK(cudaMalloc(&c->d_ppartials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
+  CK(cudaMalloc(&c->d_pfinal, 32 * sizeof(double)));
   CK(cudaMalloc(&c->d_bandcnt, 64 * sizeof(u64)));
   CK(cudaHostAlloc(&c->h_stage, 4096, cudaHostAllocDefault));
   *out = c;
@@ -1260,6 +1262,7 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
   cudaFree(c->d_noncontig);
   cudaFree(c->d_winacc); cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
+  cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
   delete c;
   return TML_OK;
@@ -1853,30 +1856,43 @@ int tml_win_bands(tml_ctx* c, const double* series, const tml_band_args* a, void
   return TML_OK;
 }
 
-int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* out) {
-  if (!c || !out || max_rows == 0) return TML_ERR_ARG;
+// Launch half: kernels + the async copy of the 16 result doubles into a private
+// staging slot.  The result is complete after ANY later synchronisation of `stream`
+// (tml_win_prepare synchronises it), so the reduce pays no separate sync for it.
+int tml_proc_reduce_launch(tml_ctx* c, uint32_t max_rows, void* stream) {
+  if (!c || max_rows == 0) return TML_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   CK(cudaSetDevice(c->device));
-  memset(out, 0, sizeof(*out));
-  out->max_ratio = -1.0;
   const u64 total = c->proc_commits.load();
   u64 n = total < c->proc_slots ? total : c->proc_slots;
   if (n > max_rows) n = max_rows;
+  c->proc_pending_n = n;
+  c->proc_pending = true;
   if (n == 0) return TML_OK;
   const u64 first_k = total - n;
   const int grid = grid_for(c, n, PR_THREADS);
-  k_proc_reduce<<<grid, PR_THREADS, 0, s>>>(c->d_pring, c->proc_slots, first_k, n, c->d_partials);
+  k_proc_reduce<<<grid, PR_THREADS, 0, s>>>(c->d_pring, c->proc_slots, first_k, n, c->d_ppartials);
   CK(cudaPeekAtLastError());
-  k_finalize<<<1, 32 * PR_COLS, 0, s>>>(c->d_partials, grid, PR_COLS, PR_MAXMASK, c->d_final);
+  k_finalize<<<1, 32 * PR_COLS, 0, s>>>(c->d_ppartials, grid, PR_COLS, PR_MAXMASK, c->d_pfinal);
   CK(cudaPeekAtLastError());
-  k_finalize_dd<<<1, 32, 0, s>>>(c->d_partials, grid, PR_COLS, 0, 15, c->d_final);
+  k_finalize_dd<<<1, 32, 0, s>>>(c->d_ppartials, grid, PR_COLS, 0, 15, c->d_pfinal);
   CK(cudaPeekAtLastError());
   c->launches += 3;
-  char* st = (char*)c->h_stage;
-  CK(cudaMemcpyAsync(st, c->d_final, PR_COLS * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpyAsync((char*)c->h_stage + 3072, c->d_pfinal, PR_COLS * sizeof(double),
+                     cudaMemcpyDeviceToHost, s));
+  return TML_OK;
+}
+
+int tml_proc_reduce_collect(tml_ctx* c, tml_proc_agg* out) {
+  if (!c || !out) return TML_ERR_ARG;
+  if (!c->proc_pending) return set_err(TML_ERR_STATE, "tml_proc_reduce_collect without a launch");
+  c->proc_pending = false;
+  memset(out, 0, sizeof(*out));
+  out->max_ratio = -1.0;
+  const u64 n = c->proc_pending_n;
+  if (n == 0) return TML_OK;
   double f[PR_COLS];
-  memcpy(f, st, sizeof(f));
+  memcpy(f, (char*)c->h_stage + 3072, sizeof(f));
   out->n = n;
   out->n_gpu = (u64)f[14];
   out->sum_cpu = f[0]; out->sum_cpu_lo = f[15]; out->max_cpu = f[4];
@@ -1889,6 +1905,14 @@ int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* o
   out->max_cores = (u32)f[12];
   out->any_gpu_available = f[13] > 0.5 ? 1u : 0u;
   return TML_OK;
+}
+
+int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* out) {
+  if (!c || !out || max_rows == 0) return TML_ERR_ARG;
+  int rc = tml_proc_reduce_launch(c, max_rows, stream);
+  if (rc != TML_OK) return rc;
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return tml_proc_reduce_collect(c, out);
 }
 
 }  // extern "C"

@@ -219,6 +219,15 @@ class Engine:
                                            C.byref(out)), "tml_win_bands")
         return out
 
+    def proc_reduce_launch(self, max_rows: int, stream: int = 0) -> None:
+        _abi.check(self._lib.tml_proc_reduce_launch(self._h, int(max_rows), stream),
+                   "tml_proc_reduce_launch")
+
+    def proc_reduce_collect(self) -> _abi.ProcAgg:
+        out = _abi.ProcAgg()
+        _abi.check(self._lib.tml_proc_reduce_collect(self._h, C.byref(out)), "tml_proc_reduce_collect")
+        return out
+
     def proc_reduce(self, max_rows: int, stream: int = 0) -> _abi.ProcAgg:
         out = _abi.ProcAgg()
         _abi.check(self._lib.tml_proc_reduce(self._h, int(max_rows), stream, C.byref(out)),

@@ -238,8 +238,15 @@ class WindowReducer:
             ev[0].record()
 
         # ---- stage 1: local windows + bounds
+        if proc_rows:  # K6 first, un-synchronised: win_prepare's sync below covers it
+            for e in self.engines:
+                if hasattr(e, "proc_reduce_launch"):
+                    e.proc_reduce_launch(max(1, int(proc_rows)), stream)
+        k3a_ev = k3a_ev0 = None
+        if ev:
+            k3a_ev0 = torch.cuda.Event(enable_timing=True)
+            k3a_ev0.record()
         local_infos = [self._info_dict(e.win_prepare(window, stream)) for e in self.engines]
-        k3a_ev = None
         if ev:
             k3a_ev = torch.cuda.Event(enable_timing=True)
             k3a_ev.record()
@@ -248,7 +255,9 @@ class WindowReducer:
         for l, d in enumerate(local_infos):
             flat.extend(self._info_pack(d))
             if proc_rows:  # process aggregates (K6) ride in the same exchange
-                a = self.engines[l].proc_reduce(max(1, int(proc_rows)), stream)
+                eng = self.engines[l]
+                a = (eng.proc_reduce_collect() if hasattr(eng, "proc_reduce_collect")
+                     else eng.proc_reduce(max(1, int(proc_rows)), stream))
                 flat.extend(float(getattr(a, f)) for f in _PROC_FIELDS)
         infos: Dict[int, Dict[str, Any]] = {}
         proc_aggs: Dict[int, Dict[str, Any]] = {}
@@ -304,7 +313,7 @@ class WindowReducer:
             for i, nm in enumerate(names):
                 timings[nm] = float(ev[i].elapsed_time(ev[i + 1]))
             timings["total"] = float(ev[0].elapsed_time(ev[4]))
-            timings["k3a"] = float(ev[0].elapsed_time(k3a_ev))
+            timings["k3a"] = float(k3a_ev0.elapsed_time(k3a_ev))
             timings["k4"] = float(sum(a.elapsed_time(b) for a, b in self._k4_events))
         if not want_series:
             pass
