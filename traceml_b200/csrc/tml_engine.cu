@@ -865,7 +865,9 @@ struct ReduceParams {
 
 #define RD_THREADS 256
 
-template <int R>
+// U rows per thread per trip: R x U independent 16-B loads are issued before any is
+// consumed, so small-R launches (R = 1, 2) still keep enough bytes in flight per SM.
+template <int R, int U>
 __global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_constant__ ReduceParams p) {
   const int q = threadIdx.x & 3;
   const u64 nthreads = (u64)gridDim.x * RD_THREADS;
@@ -873,51 +875,60 @@ __global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_const
   const u64 n = p.n_common;
   double* __restrict__ S = p.series;
   const bool do_time = (p.mask & TML_MASK_TIME) != 0u, do_mem = (p.mask & TML_MASK_MEM) != 0u;
-  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads) {
-    const u64 t = tb + threadIdx.x;
-    const bool ok = t < work;  // block-uniform trip count keeps the shuffles full-warp
-    const u64 j = p.shard_lo + (t >> 2);
-    double x[R], y[R];
-    // R independent 16-B loads in flight per thread (local HBM or NVLink peer)
+  // block-uniform trip count keeps the width-4 shuffles full-warp
+  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads * U) {
+    double x[U][R], y[U][R];
+    bool ok[U];
+    u64 jj[U];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (ok) v = __ldg(&p.rows[r][j * 4 + q]);
-      double2 d = *reinterpret_cast<double2*>(&v);
-      x[r] = d.x; y[r] = d.y;
+    for (int u = 0; u < U; ++u) {
+      const u64 t = tb + (u64)u * nthreads + threadIdx.x;
+      ok[u] = t < work;
+      jj[u] = p.shard_lo + (t >> 2);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {  // local HBM or NVLink peer loads
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ok[u]) v = __ldg(&p.rows[r][jj[u] * 4 + q]);
+        double2 d = *reinterpret_cast<double2*>(&v);
+        x[u][r] = d.x; y[u][r] = d.y;
+      }
     }
-    double z[R];  // q2: wait_proxy
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      double fb = shfl_idx_f64(x[r] + y[r], 1, 4);   // fwd + bwd from q1
-      if (q == 2) {
-        const double compute = fb + x[r];            // (fwd + bwd) + opt
-        const double traced = fmax(y[r], compute);   // model.py:246
-        z[r] = fmax(0.0, traced - compute);          // model.py:247
-        y[r] = traced;
+    for (int u = 0; u < U; ++u) {
+      double z[R];  // q2: wait_proxy
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double fb = shfl_idx_f64(x[u][r] + y[u][r], 1, 4);   // fwd + bwd from q1
+        if (q == 2) {
+          const double compute = fb + x[u][r];               // (fwd + bwd) + opt
+          const double traced = fmax(y[u][r], compute);      // model.py:246
+          z[r] = fmax(0.0, traced - compute);                // model.py:247
+          y[u][r] = traced;
+        } else {
+          z[r] = 0.0;
+        }
+      }
+      if (!ok[u]) continue;
+      const u64 j = jj[u];
+      double med, mx;
+      if (q == 0) {
+        if (do_time) { median_max<R>(x[u], med, mx); S[0 * n + j] = med; S[1 * n + j] = mx; }
+      } else if (q == 1) {
+        if (do_time) {
+          median_max<R>(x[u], med, mx); S[2 * n + j] = med; S[3 * n + j] = mx;
+          median_max<R>(y[u], med, mx); S[4 * n + j] = med; S[5 * n + j] = mx;
+        }
+      } else if (q == 2) {
+        if (do_time) {
+          median_max<R>(x[u], med, mx); S[6 * n + j] = med; S[7 * n + j] = mx;
+          median_max<R>(y[u], med, mx); S[8 * n + j] = med; S[9 * n + j] = mx;
+          median_max<R>(z, med, mx); S[10 * n + j] = med; S[11 * n + j] = mx;
+        }
       } else {
-        z[r] = 0.0;
-      }
-    }
-    if (!ok) continue;
-    double med, mx;
-    if (q == 0) {
-      if (do_time) { median_max<R>(x, med, mx); S[0 * n + j] = med; S[1 * n + j] = mx; }
-    } else if (q == 1) {
-      if (do_time) {
-        median_max<R>(x, med, mx); S[2 * n + j] = med; S[3 * n + j] = mx;
-        median_max<R>(y, med, mx); S[4 * n + j] = med; S[5 * n + j] = mx;
-      }
-    } else if (q == 2) {
-      if (do_time) {
-        median_max<R>(x, med, mx); S[6 * n + j] = med; S[7 * n + j] = mx;
-        median_max<R>(y, med, mx); S[8 * n + j] = med; S[9 * n + j] = mx;
-        median_max<R>(z, med, mx); S[10 * n + j] = med; S[11 * n + j] = mx;
-      }
-    } else {
-      if (do_mem) {
-        median_max<R>(x, med, mx); S[12 * n + j] = med; S[13 * n + j] = mx;
-        median_max<R>(y, med, mx); S[14 * n + j] = med; S[15 * n + j] = mx;
+        if (do_mem) {
+          median_max<R>(x[u], med, mx); S[12 * n + j] = med; S[13 * n + j] = mx;
+          median_max<R>(y[u], med, mx); S[14 * n + j] = med; S[15 * n + j] = mx;
+        }
       }
     }
   }
@@ -1788,7 +1799,8 @@ int tml_peer_close(tml_ctx* c, void* peer_ptr) {
 
 template <int R>
 static void launch_reduce(int grid, cudaStream_t s, const ReduceParams& p) {
-  k_window_reduce<R><<<grid, RD_THREADS, 0, s>>>(p);
+  constexpr int U = (R <= 2) ? 4 : (R <= 4 ? 2 : 1);
+  k_window_reduce<R, U><<<grid, RD_THREADS, 0, s>>>(p);
 }
 
 extern "C" {
