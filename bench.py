@@ -257,6 +257,23 @@ def step_overhead(device, world, local, quick=False):
         out["telemetry_rate"] = {"step_records_per_s": n_rec / dt, "step_records_drained": got,
                                  "proc_samples_per_s": n_rec / dt2, "proc_samples_drained": pgot,
                                  "records": n_rec}
+        # BASELINE config 4: native sampler thread at 1 kHz for one second, GIL kept busy
+        try:
+            from traceml_b200.utils import timing as _tm
+
+            if _tm._FAST is not None:
+                eng.proc_drain()
+                _tm._FAST.sampler_start(1000, 0)
+                t2, spin = time.perf_counter(), 0
+                while time.perf_counter() - t2 < 1.0:
+                    spin += 1
+                last, late = _tm._FAST.sampler_stop()
+                el = time.perf_counter() - t2
+                out["telemetry_rate"]["native_sampler"] = {
+                    "requested_hz": 1000, "achieved_hz": last / el, "late_periods": late,
+                    "drained": len(eng.proc_drain()[0])}
+        except Exception as exc:
+            out["telemetry_rate"]["native_sampler"] = {"error": str(exc)}
     except Exception as exc:
         out["api_cost_us"] = {"error": str(exc)}
 

@@ -163,3 +163,33 @@ def test_failed_step_flushes_under_old_id(cuda):
     recs, _ = eng.drain()
     assert runtime.get_trace_session_state().step == before   # not advanced
     assert len(recs) == 1 and int(recs["step"][0]) == before  # flushed under the old id
+
+
+def test_native_process_sampler_1khz(cuda):
+    """BASELINE config 4: 1 kHz process telemetry from the C++ sampler thread (no GIL)."""
+    import traceml_b200 as traceml
+    from traceml_b200 import runtime
+    from traceml_b200.runtime import TraceMLRuntime
+
+    traceml.init(mode="auto")
+    eng = runtime.get_engine()
+    eng.proc_drain()
+    rt = TraceMLRuntime(interval_sec=0.05, native_process_hz=1000.0)
+    rt.start()
+    t0 = time.perf_counter()
+    x = torch.randn(1024, 1024, device="cuda")
+    while time.perf_counter() - t0 < 0.6:   # keep the GIL busy, as a training loop would
+        x = (x @ x).tanh()
+    rt.stop()
+    torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    recs, dropped = eng.proc_drain()
+    total = rt.native_samples
+    assert dropped == 0
+    assert 0.7 * 1000 * elapsed < total < 1.2 * 1000 * elapsed, (total, elapsed)
+    assert eng.proc_count >= total
+    if len(recs) > 1:
+        assert (np.diff(recs["seq"].astype(np.int64)) == 1).all()
+        assert (recs["rss"] > 0).all() and (recs["mem_total"] > 0).all()
+        assert (recs["flags"] == 3).all() and (recs["cpu_pct"] >= 0).all()
+        assert np.median(np.diff(recs["ts"])) == pytest.approx(1e-3, rel=0.25)

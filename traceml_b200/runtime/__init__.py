@@ -117,10 +117,14 @@ class TraceMLRuntime:
     """
 
     def __init__(self, interval_sec: float = 2.0, sinks: Optional[List[Callable]] = None,
-                 sample_process: bool = True):
+                 sample_process: bool = True, native_process_hz: float = 0.0):
         self.interval = max(1e-4, float(interval_sec))
         self.sinks = list(sinks or [])
         self.sample_process = sample_process
+        # > 0: the C++ sampler thread (no GIL) commits process samples at this rate and the
+        # Python tick only drains; 0: one sample per tick from Python (the reference cadence)
+        self.native_process_hz = float(native_process_hz)
+        self._native = None
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
         self._proc = None
@@ -133,7 +137,17 @@ class TraceMLRuntime:
             return
         from ..samplers import ProcessProbe
 
-        self._proc = ProcessProbe() if self.sample_process else None
+        self._proc = None
+        if self.sample_process and self.native_process_hz > 0:
+            from ..utils import timing
+
+            timing._ENG or timing._resolve()
+            if timing._FAST is None:
+                raise RuntimeError("native process sampler needs the _tml_step extension")
+            self._native = timing._FAST
+            self._native.sampler_start(int(round(1.0e6 / self.native_process_hz)), 0)
+        elif self.sample_process:
+            self._proc = ProcessProbe()
         self._thread = threading.Thread(target=self._loop, name="traceml-b200-sampler", daemon=True)
         self._thread.start()
 
@@ -168,6 +182,9 @@ class TraceMLRuntime:
         self._stop.set()
         self._thread.join(timeout=5.0)
         self._thread = None
+        if self._native is not None:
+            self.native_samples, self.native_late = self._native.sampler_stop()
+            self._native = None
         try:
             self._tick()  # final drain (runtime/runtime.py:163-193)
         except Exception as exc:
