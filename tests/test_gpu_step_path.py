@@ -193,3 +193,86 @@ def test_native_process_sampler_1khz(cuda):
         assert (recs["rss"] > 0).all() and (recs["mem_total"] > 0).all()
         assert (recs["flags"] == 3).all() and (recs["cpu_pct"] >= 0).all()
         assert np.median(np.diff(recs["ts"])) == pytest.approx(1e-3, rel=0.25)
+
+
+def test_lightning_style_seam_sequence(cuda):
+    """The kept Lightning callback drives the seam by hand
+    (integrations/lightning.py:59-190): timed_region.__enter__/__exit__ across hooks, a
+    zero-duration optimizer event on accumulation micro-steps, StepMemoryTracker,
+    advance_step, flush_step_events.  Same calls against this package's seam."""
+    import traceml_b200 as traceml
+    from traceml_b200 import runtime
+    from traceml_b200.runtime.state import get_trace_session_state
+    from traceml_b200.utils.flush_buffers import flush_step_events
+    from traceml_b200.utils.step_memory import StepMemoryTracker
+    from traceml_b200.utils.timing import TimeEvent, TimeScope, record_event, timed_region
+
+    traceml.init(mode="auto")
+    eng = runtime.get_engine()
+    torch.cuda.synchronize()
+    eng.drain()
+    model = torch.nn.Linear(64, 64).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    state = get_trace_session_state()
+    first = state.step
+    for micro in range(4):
+        step_ctx = timed_region("_traceml_internal:step_time", scope="step", use_gpu=False)
+        step_ctx.__enter__()
+        tracker = StepMemoryTracker(model)
+        tracker.reset()
+        fwd = timed_region("_traceml_internal:forward_time", scope="step")
+        fwd.__enter__()
+        loss = model(torch.randn(8, 64, device="cuda")).square().mean()
+        fwd.__exit__(None, None, None)
+        bwd = timed_region("_traceml_internal:backward_time", scope="step")
+        bwd.__enter__()
+        torch.autograd.backward(loss)
+        bwd.__exit__(None, None, None)
+        stepped = micro % 2 == 1
+        if stepped:
+            o = timed_region("_traceml_internal:optimizer_step", scope="step")
+            o.__enter__()
+            opt.step()
+            opt.zero_grad()
+            o.__exit__(None, None, None)
+        step_ctx.__exit__(None, None, None)
+        if not stepped:  # accumulation micro-step: dummy 0-duration optimizer event
+            record_event(TimeEvent(name="_traceml_internal:optimizer_step", device="cpu", cpu_start=0.0,
+                                   cpu_end=0.0, gpu_time_ms=0.0, resolved=True, scope=TimeScope.STEP))
+        tracker.record()
+        state.advance_step()
+        flush_step_events(model, state.step)
+    torch.cuda.synchronize()
+    recs, _ = eng.drain()
+    assert list(recs["step"]) == [first + 1, first + 2, first + 3, first + 4]
+    # every micro-step carries an optimizer event (real or dummy) so steps stay aligned
+    assert (recs["n_calls"][:, 4] >= 1).all()
+    assert int(recs["dur_ns"][0, 4]) == 0 and int(recs["dur_ns"][1, 4]) > 0
+    assert (recs["flags"] == 1).all() and (recs["n_calls"][:, 5] == 1).all()
+
+
+def test_regions_on_a_side_stream_and_graph_capture(cuda):
+    """Stamps follow the CURRENT stream; under CUDA-graph capture the region degrades to the
+    host clock instead of inserting kernels into the graph."""
+    from traceml_b200.engine import Engine
+    from traceml_b200 import _abi
+
+    eng = Engine(device=0, ring_slots=64)
+    side = torch.cuda.Stream()
+    x = torch.zeros(1 << 22, device="cuda")
+    with torch.cuda.stream(side):
+        slot = eng.phase_begin(2, side.cuda_stream)
+        x += 1
+        assert eng.phase_end(2, slot, side.cuda_stream) == 0
+        assert eng.step_commit(1, 0, 0, 0, 0.0, side.cuda_stream) == 0
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    cap = torch.cuda.Stream()
+    with torch.cuda.stream(cap):
+        with torch.cuda.graph(g, stream=cap):
+            assert eng.phase_begin(2, cap.cuda_stream) == _abi.TML_ERR_CAPTURE
+            x += 1
+    torch.cuda.synchronize()
+    recs, _ = eng.drain()
+    assert len(recs) == 1 and int(recs["dur_ns"][0, 2]) > 0
+    eng.close()
