@@ -276,3 +276,38 @@ def test_regions_on_a_side_stream_and_graph_capture(cuda):
     recs, _ = eng.drain()
     assert len(recs) == 1 and int(recs["dur_ns"][0, 2]) > 0
     eng.close()
+
+
+def test_step_path_never_waits_for_the_gpu(cuda):
+    """No host synchronisation on the step path: with ~0.4 s of GPU work queued ahead, a
+    whole traced step (regions, allocator counters, commit) returns in milliseconds and the
+    stream is still busy afterwards."""
+    import traceml_b200 as traceml
+    from traceml_b200 import runtime
+
+    traceml.init(mode="auto")
+    eng = runtime.get_engine()
+    model = torch.nn.Linear(32, 32).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    x = torch.randn(16, 32).pin_memory()
+    with traceml.trace_step(model):   # warm-up: engine creation, lazy inits
+        model(x.to("cuda", non_blocking=True)).sum().backward()
+        opt.step()
+    torch.cuda.synchronize()
+    eng.drain()
+    torch.cuda._sleep(int(0.4 * 1.9e9))          # ~0.4 s of device time ahead of us
+    t0 = time.perf_counter()
+    with traceml.trace_step(model):
+        xd = x.to("cuda", non_blocking=True)
+        loss = model(xd).sum()
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    busy = not torch.cuda.current_stream().query()
+    assert busy, "the queued GPU work already finished: the test could not observe a wait"
+    assert host_ms < 60.0, f"traced step blocked the host for {host_ms:.1f} ms"
+    assert len(eng.drain()[0]) == 0              # the record is not committed yet ...
+    torch.cuda.synchronize()
+    recs, _ = eng.drain()                        # ... and appears once the stream catches up
+    assert len(recs) == 1 and int(recs["n_calls"][0, 2]) == 1
