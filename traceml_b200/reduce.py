@@ -233,6 +233,9 @@ class WindowReducer:
         R = self.comm.world * self.L
         ev = None
         timings: Dict[str, float] = {}
+        import time as _time
+
+        hw = [_time.perf_counter()]
         if dev.type == "cuda":
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             ev[0].record()
@@ -271,6 +274,7 @@ class WindowReducer:
                         pa[f] = int(round(pa[f]))
                     proc_aggs[p * self.L + l] = pa
         ranks = sorted(infos)
+        hw.append(_time.perf_counter())
         if ev:
             ev[1].record()
 
@@ -285,6 +289,7 @@ class WindowReducer:
                                windows=dict(t_res.windows))
         else:
             m_res = self._align(KIND_MEM, window, infos, ranks, stream)
+        hw.append(_time.perf_counter())
         if ev:
             ev[2].record()
 
@@ -301,11 +306,15 @@ class WindowReducer:
                 self._reduce_pass(KIND_TIME, _abi.MASK_TIME, t_res, stream, mode)
             if m_res.n_common:
                 self._reduce_pass(KIND_MEM, _abi.MASK_MEM, m_res, stream, mode)
+        hw.append(_time.perf_counter())
         if ev:
             ev[3].record()
 
         # ---- stage 5: trend bands
         self._bands(t_res, m_res, same, stream)
+        hw.append(_time.perf_counter())
+        for i, nm in enumerate(("prepare", "align", "reduce", "bands")):
+            timings["host_" + nm] = (hw[i + 1] - hw[i]) * 1e3
         if ev:
             ev[4].record()
             torch.cuda.synchronize(dev)
