@@ -209,6 +209,7 @@ typedef struct tml_win_info {
   /* per kind: 1 if every window row is a candidate and their step ids are
    * consecutive (then tml_win_select_dense applies)                          */
   uint32_t dense[2];
+  double kernel_ms;      /* device time of k_window_rows alone (CUDA events)   */
 } tml_win_info;
 
 /* Stage 1 (local).  Linearises the ring into WindowRows (ns -> ms), step ids

@@ -50,7 +50,7 @@ class LiveStats(C.Structure):
 class WinInfo(C.Structure):
     _fields_ = [("n_retained", u64), ("latest_step", u64), ("monotone", u32), ("dup_rows", u32),
                 ("n_rows", u64 * 2), ("n_cand", u64 * 2), ("lo", u64 * 2), ("hi", u64 * 2),
-                ("t_sums", f64 * 7), ("t_count", u64), ("n_both", u64), ("dense", u32 * 2)]
+                ("t_sums", f64 * 7), ("t_count", u64), ("n_both", u64), ("dense", u32 * 2), ("kernel_ms", f64)]
 
 
 class AlignInfo(C.Structure):

@@ -372,10 +372,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// one warp fetches its 32-record tile: 8 x cp.async per lane, each instruction = 512 B contiguous
+// one warp fetches its 32-record tile: 8 x cp.async per lane, each instruction = 512 B contiguous.
+// slot0 = ring slot of the tile's first record (maintained incrementally by the caller).
 __device__ __forceinline__ void wr_issue_warp(uint4* buf, const uint4* __restrict__ ring4, u32 ring_slots,
-                                              u64 first_k, u64 n, u64 base, int lane) {
-  const u64 slot0 = (first_k + base) % ring_slots;  // one 64-bit modulo per tile, then add-and-wrap
+                                              u64 slot0, u64 n, u64 base, int lane) {
+  if (base + 32 <= n && slot0 + 32 <= (u64)ring_slots) {  // whole tile, no ring wrap: linear addresses
+    const uint4* src = ring4 + slot0 * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int idx = c * 32 + lane;
+      cp_async16(&buf[(idx & ~7) | ((idx ^ (idx >> 3)) & 7)], src + idx);
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int idx = c * 32 + lane;
@@ -414,7 +423,11 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
   uint4* rows4 = reinterpret_cast<uint4*>(rows);
 
   u64 wt = (u64)blockIdx.x * WR_WARPS + warp;
-  if (wt < nwt) wr_issue_warp(w_in0, ring4, ring_slots, first_k, n, wt * 32, lane);
+  // ring slot of this warp's current tile and the per-trip advance, both kept < ring_slots:
+  // two 64-bit modulos per warp for the whole kernel instead of one per lane per tile
+  u64 slot_cur = (first_k + wt * 32) % ring_slots;
+  const u64 slot_adv = (wstride * 32) % ring_slots;
+  if (wt < nwt) wr_issue_warp(w_in0, ring4, ring_slots, slot_cur, n, wt * 32, lane);
   cp_async_commit();
 
   for (int it = 0; wt < nwt; wt += wstride, ++it) {
@@ -422,16 +435,21 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     uint4* nxt = (it & 1) ? w_in0 : w_in1;
     const u64 base = wt * 32;
     const u64 next = wt + wstride;
-    if (next < nwt) wr_issue_warp(nxt, ring4, ring_slots, first_k, n, next * 32, lane);
+    u64 slot_next = slot_cur + slot_adv;
+    if (slot_next >= ring_slots) slot_next -= ring_slots;
+    if (next < nwt) wr_issue_warp(nxt, ring4, ring_slots, slot_next, n, next * 32, lane);
     cp_async_commit();
     // tile-edge neighbours (first/last-of-step tests) straight from the ring
     u64 halo_step = 0;
     u32 halo_flags = 0;
-    if (lane == 0 && base > 0) halo_step = ring[(first_k + base - 1) % ring_slots].step;
+    if (lane == 0 && base > 0) halo_step = ring[slot_cur == 0 ? ring_slots - 1 : slot_cur - 1].step;
     if (lane == 31 && base + 32 < n) {
-      const tml_step_record* p = &ring[(first_k + base + 32) % ring_slots];
+      u64 hs = slot_cur + 32;
+      while (hs >= ring_slots) hs -= ring_slots;
+      const tml_step_record* p = &ring[hs];
       halo_step = p->step; halo_flags = p->flags;
     }
+    slot_cur = slot_next;
     cp_async_wait<1>();  // this tile has landed; the next one stays in flight
     __syncwarp();
 
@@ -508,12 +526,21 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       w_out[lane * 4 + (3 ^ so)] = *reinterpret_cast<uint4*>(&o3);
     }
     __syncwarp();
+    if (base + 32 <= n) {
+      uint4* dst = rows4 + base * 4;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int idx = c * 32 + lane;
-      const int r = idx >> 2, q = idx & 3;
-      const u64 ii = base + (u64)r;
-      if (ii < n) rows4[ii * 4 + q] = w_out[r * 4 + (q ^ ((r >> 1) & 3))];
+      for (int c = 0; c < 4; ++c) {
+        const int idx = c * 32 + lane;
+        dst[idx] = w_out[(idx & ~3) | ((idx ^ (idx >> 3)) & 3)];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int idx = c * 32 + lane;
+        const int r = idx >> 2, q = idx & 3;
+        const u64 ii = base + (u64)r;
+        if (ii < n) rows4[ii * 4 + q] = w_out[r * 4 + (q ^ ((r >> 1) & 3))];
+      }
     }
     __syncwarp();  // w_out and `cur` are free again
   }
@@ -1152,6 +1179,7 @@ struct tml_ctx {
   tml_step_record* h_mirror = nullptr; tml_step_record* d_mirror = nullptr;
   tml_proc_record* h_pmirror = nullptr; tml_proc_record* d_pmirror = nullptr;
   // host-side step state (training thread)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of k_window_rows alone
   u64 commits = 0;
   u64 launches = 0;  // kernels this context has launched (bench: gpu_launches)
   u32 next_slot = 0;
@@ -1529,10 +1557,13 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   }
   int grid = (int)((n + WR_THREADS - 1) / WR_THREADS);
   if (grid > c->n_sms * 2) grid = c->n_sms * 2;  // 2 resident CTAs per SM (83 KB smem each)
+  if (!c->ev0) { CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); }
+  CK(cudaEventRecord(c->ev0, s));
   k_window_rows<<<grid, WR_THREADS, WR_SMEM_BYTES, s>>>(c->d_ring, c->ring_slots, first_k, n, c->win_tstart,
                                             c->d_rows, c->d_steps, c->d_flags, c->d_winacc,
                                             c->d_partials);
   CK(cudaPeekAtLastError());
+  CK(cudaEventRecord(c->ev1, s));
   k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
   CK(cudaPeekAtLastError());
   k_copy7<<<1, 32, 0, s>>>(c->d_final + 32, c->d_final);
@@ -1565,6 +1596,10 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   }
   out->t_count = acc.t_count;
   out->n_both = acc.n_both;
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->kernel_ms = (double)ms;
+  }
   c->win_ncand[0] = acc.ncand[0]; c->win_ncand[1] = acc.ncand[1];
   // dense: every window row is a candidate and the candidates' step ids are consecutive, so
   // row(step) = first_row + (step - lo) and the aligned rows are a contiguous slice
