@@ -369,24 +369,26 @@ class WindowReducer:
     def _align_pack(self, engine, kind, a) -> List[float]:
         """15 numbers + (p2p only) the rows' CUDA-IPC handle, so the peer mapping
         needs no collective of its own."""
-        handle = bytes(72)
-        if self._exchange_mode() == "p2p" and int(a.n_rows) > 0:
-            handle = engine.win_rows_export(kind)
-        return ([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
-                + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums]
-                + [float(b) for b in handle])
+        out = ([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
+               + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
+        if self._exchange_mode() == "p2p":
+            handle = engine.win_rows_export(kind) if int(a.n_rows) > 0 else bytes(72)
+            out += [float(b) for b in handle]
+        return out
 
     def _collect_aligns(self, kind, res, flat, part, infos) -> KindResult:
         res.handles = {}
         gathered = []
+        p2p = self._exchange_mode() == "p2p"
+        alen = _ALIGN_LEN if p2p else 15
         for row in self.comm.all_gather_vec(flat, self.device):
             lst = []
             for l in range(self.L):
-                v = row[l * _ALIGN_LEN:(l + 1) * _ALIGN_LEN]
+                v = row[l * alen:(l + 1) * alen]
                 lst.append({"n_common": int(round(v[0])), "start": int(round(v[1])),
                             "end": int(round(v[2])), "n_rows": int(round(v[3])),
                             "t_sums": list(v[4:11]), "m_sums": list(v[11:15]),
-                            "handle": bytes(int(round(b)) for b in v[15:87])})
+                            "handle": bytes(int(round(b)) for b in v[15:87]) if p2p else b""})
             gathered.append(lst)
         n_common = max(a["n_common"] for lst in gathered for a in lst)
         res.n_common = n_common
