@@ -892,72 +892,76 @@ struct ReduceParams {
 
 #define RD_THREADS 256
 
-// U rows per thread per trip: R x U independent 16-B loads are issued before any is
-// consumed, so small-R launches (R = 1, 2) still keep enough bytes in flight per SM.
+// Tile = 64 steps per CTA trip (256 threads = 64 steps x 4 chunks).  Results are staged
+// in shared memory as [16 series][64 steps] and leave as 256-B contiguous warp stores
+// (warp w writes series 2w and 2w+1), instead of sixteen 64-B fragments per warp: the
+// kernel writes twice what it reads at small R, so store locality decides its HBM
+// efficiency.
 template <int R, int U>
 __global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_constant__ ReduceParams p) {
-  const int q = threadIdx.x & 3;
+  __shared__ double s_out[TML_SERIES_PER_STEP][RD_THREADS / 4];
+  const int q = threadIdx.x & 3, row = threadIdx.x >> 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u64 nthreads = (u64)gridDim.x * RD_THREADS;
   const u64 work = (p.shard_hi - p.shard_lo) * 4ull;
   const u64 n = p.n_common;
   double* __restrict__ S = p.series;
   const bool do_time = (p.mask & TML_MASK_TIME) != 0u, do_mem = (p.mask & TML_MASK_MEM) != 0u;
-  // block-uniform trip count keeps the width-4 shuffles full-warp
-  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads * U) {
-    double x[U][R], y[U][R];
-    bool ok[U];
-    u64 jj[U];
+  // block-uniform trip count: the width-4 shuffles and the barriers need every thread
+  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads) {
+    const u64 t = tb + threadIdx.x;
+    const bool ok = t < work;
+    const u64 j = p.shard_lo + (t >> 2);
+    double x[R], y[R], z[R];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const u64 t = tb + (u64)u * nthreads + threadIdx.x;
-      ok[u] = t < work;
-      jj[u] = p.shard_lo + (t >> 2);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {  // local HBM or NVLink peer loads
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (ok[u]) v = __ldg(&p.rows[r][jj[u] * 4 + q]);
-        double2 d = *reinterpret_cast<double2*>(&v);
-        x[u][r] = d.x; y[u][r] = d.y;
-      }
+    for (int r = 0; r < R; ++r) {  // R independent 16-B loads in flight: local HBM or NVLink peer
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) v = __ldg(&p.rows[r][j * 4 + q]);
+      double2 d = *reinterpret_cast<double2*>(&v);
+      x[r] = d.x; y[r] = d.y;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      double z[R];  // q2: wait_proxy
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        double fb = shfl_idx_f64(x[u][r] + y[u][r], 1, 4);   // fwd + bwd from q1
-        if (q == 2) {
-          const double compute = fb + x[u][r];               // (fwd + bwd) + opt
-          const double traced = fmax(y[u][r], compute);      // model.py:246
-          z[r] = fmax(0.0, traced - compute);                // model.py:247
-          y[u][r] = traced;
-        } else {
-          z[r] = 0.0;
-        }
-      }
-      if (!ok[u]) continue;
-      const u64 j = jj[u];
-      double med, mx;
-      if (q == 0) {
-        if (do_time) { median_max<R>(x[u], med, mx); S[0 * n + j] = med; S[1 * n + j] = mx; }
-      } else if (q == 1) {
-        if (do_time) {
-          median_max<R>(x[u], med, mx); S[2 * n + j] = med; S[3 * n + j] = mx;
-          median_max<R>(y[u], med, mx); S[4 * n + j] = med; S[5 * n + j] = mx;
-        }
-      } else if (q == 2) {
-        if (do_time) {
-          median_max<R>(x[u], med, mx); S[6 * n + j] = med; S[7 * n + j] = mx;
-          median_max<R>(y[u], med, mx); S[8 * n + j] = med; S[9 * n + j] = mx;
-          median_max<R>(z, med, mx); S[10 * n + j] = med; S[11 * n + j] = mx;
-        }
+    for (int r = 0; r < R; ++r) {
+      double fb = shfl_idx_f64(x[r] + y[r], 1, 4);   // fwd + bwd from q1
+      if (q == 2) {
+        const double compute = fb + x[r];            // (fwd + bwd) + opt
+        const double traced = fmax(y[r], compute);   // model.py:246
+        z[r] = fmax(0.0, traced - compute);          // model.py:247
+        y[r] = traced;
       } else {
-        if (do_mem) {
-          median_max<R>(x[u], med, mx); S[12 * n + j] = med; S[13 * n + j] = mx;
-          median_max<R>(y[u], med, mx); S[14 * n + j] = med; S[15 * n + j] = mx;
+        z[r] = 0.0;
+      }
+    }
+    double med, mx;
+    if (q == 0) {
+      median_max<R>(x, med, mx); s_out[0][row] = med; s_out[1][row] = mx;
+    } else if (q == 1) {
+      median_max<R>(x, med, mx); s_out[2][row] = med; s_out[3][row] = mx;
+      median_max<R>(y, med, mx); s_out[4][row] = med; s_out[5][row] = mx;
+    } else if (q == 2) {
+      median_max<R>(x, med, mx); s_out[6][row] = med; s_out[7][row] = mx;
+      median_max<R>(y, med, mx); s_out[8][row] = med; s_out[9][row] = mx;
+      median_max<R>(z, med, mx); s_out[10][row] = med; s_out[11][row] = mx;
+    } else {
+      median_max<R>(x, med, mx); s_out[12][row] = med; s_out[13][row] = mx;
+      median_max<R>(y, med, mx); s_out[14][row] = med; s_out[15][row] = mx;
+    }
+    __syncthreads();
+    {
+      const u64 tile_j = p.shard_lo + (tb >> 2);           // first step of this tile
+      const u64 left = p.shard_hi - tile_j;                // steps of the tile that exist
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int sidx = warp * 2 + k;
+        const bool on = sidx < 12 ? do_time : do_mem;
+        if (on) {
+          double* dst = S + (u64)sidx * n + tile_j;
+          if ((u64)lane < left) dst[lane] = s_out[sidx][lane];
+          if ((u64)lane + 32 < left) dst[lane + 32] = s_out[sidx][lane + 32];
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -1138,14 +1142,20 @@ __global__ void __launch_bounds__(PR_THREADS) k_proc_reduce(const tml_proc_recor
   }
 }
 
-// fold the per-CTA (hi, lo) cpu sums in CTA order with TwoSum -> out[0], out[15]
+// fold the per-CTA (hi, lo) cpu sums with TwoSum -> out[hi_col], out[lo_col]: one warp,
+// lane l folds CTAs l, l+32, ... then a shuffle tree of double-double adds (fixed order)
 __global__ void k_finalize_dd(const double* __restrict__ partials, int nblk, int ncols, int hi_col,
                               int lo_col, double* __restrict__ out) {
-  if (threadIdx.x != 0) return;
+  const int lane = threadIdx.x & 31;
   double h = 0.0, l = 0.0;
-  for (int b = 0; b < nblk; ++b) dd_add(h, l, partials[(size_t)b * ncols + hi_col], partials[(size_t)b * ncols + lo_col]);
-  out[hi_col] = h;
-  out[lo_col] = l;
+  for (int b = lane; b < nblk; b += 32)
+    dd_add(h, l, partials[(size_t)b * ncols + hi_col], partials[(size_t)b * ncols + lo_col]);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const double oh = shfl_xor_f64(h, m), ol = shfl_xor_f64(l, m);
+    dd_add(h, l, oh, ol);
+  }
+  if (lane == 0) { out[hi_col] = h; out[lo_col] = l; }
 }
 
 // =================================================================== host side
