@@ -436,8 +436,16 @@ def main():
                           "GBps": k3a_bytes / (med["k3a"] * 1e-3) / 1e9 if med.get("k3a") else None},
     }
     dom = max(kernels, key=lambda k: kernels[k]["ms"] or 0.0)
+    traffic = None
+    try:  # DRAM traffic per launch from the committed ncu capture, if it is this workload
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("window") == W and tj.get("ranks") == R and dom in tj:
+            traffic = tj[dom]["dram_read_bytes"] + tj[dom]["dram_write_bytes"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak,
-                "unit": "GB/s", "frac": (kernels[dom]["GBps"] or 0.0) / peak, "traffic": None,
+                "unit": "GB/s", "frac": (kernels[dom]["GBps"] or 0.0) / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernels": kernels, "stage_ms": med}
 
     # ---- (2) end to end from HOST buffers: H2D + reduce + results on the host
@@ -491,6 +499,9 @@ def main():
                        "l2": "inputs larger than L2 (ring 512 MB/rank at W=4e6); no flush needed",
                        "algorithmic_bytes_per_step": b_reduce(R, W)},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "records_per_s": R * W / (ms_step * 1e-3),
+            "scaling_note": "weak: every rank holds W records; by the SURVEY formula the bytes grow as "
+                            "(64 R + 128) W, so constant step time gives value(N)/value(1) = (64 N + 128)/192",
             "roofline": roofline, "cpu_baseline": cpu, "step_overhead": overhead,
             "diagnosis": st["primary"]["status"] if st else None,
         }
