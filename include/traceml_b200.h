@@ -341,6 +341,54 @@ int tml_proc_reduce(tml_ctx* ctx, uint32_t max_rows, void* stream,
 int tml_proc_reduce_launch(tml_ctx* ctx, uint32_t max_rows, void* stream);
 int tml_proc_reduce_collect(tml_ctx* ctx, tml_proc_agg* out);
 
+/* ---------------------------------------------------------------- LIVE TICK
+ * The render-tick twin of the window reduce: what the reference's live CLI /
+ * dashboard recompute every second from SQLite (StepCombinedComputer,
+ * renderers/step_time/compute.py:129-315).  Same staging as the reduce above,
+ * over the last `lookback = 4 x window` records (compute.py:366-368):
+ *   prepare  -> rows of the look-back records; candidate = newest row of a step id
+ *               (compute.py:371-401); bounds for the intersection
+ *   presence -> bytes over [glo, glo+span); caller MIN-all-reduces them
+ *   select   -> last `window` common step ids (compute.py:452-470), this rank's
+ *               rows for them, and their six raw window sums in ascending step
+ *               order (compute.py:502-531: dl, h2d, fwd, bwd, opt, step wall)
+ *   series   -> per-step median / worst / sum across ranks (compute.py:573-596)
+ * Runs on any stream, concurrently with the step path (the ring head is read on
+ * the device; nothing here touches the training stream).                      */
+typedef struct tml_combined_info {
+  uint64_t n_rows;      /* look-back rows read from the ring                  */
+  uint64_t n_cand;      /* distinct step ids among them                       */
+  uint64_t lo, hi;      /* min / max candidate step id (valid if n_cand > 0)  */
+  uint64_t latest_step; /* max step id: min over ranks = completed_step       */
+  uint32_t monotone;
+  uint32_t _pad;
+} tml_combined_info;
+
+typedef struct tml_combined_align {
+  uint64_t n_common;    /* steps_used (<= window), identical on every rank    */
+  uint64_t n_rows;      /* this rank's rows for them (0 if it has no rows)    */
+  double sums[6];       /* dl, h2d, fwd, bwd, opt, step wall (ms)             */
+} tml_combined_align;
+
+int tml_combined_prepare(tml_ctx* ctx, uint32_t lookback, void* stream,
+                         tml_combined_info* out);
+int tml_combined_presence(tml_ctx* ctx, uint64_t glo, uint64_t span,
+                          uint8_t* presence_dev, void* stream);
+int tml_combined_select(tml_ctx* ctx, uint64_t glo, uint64_t span,
+                        const uint8_t* presence_dev, uint32_t window,
+                        void* stream, tml_combined_align* out);
+/* this rank's aligned rows (n_common x 64 B, ascending step id), or NULL */
+const void* tml_combined_rows(tml_ctx* ctx);
+/* the n_common aligned step ids -> host buffer */
+int tml_combined_steps(tml_ctx* ctx, uint64_t* steps_host, uint64_t cap,
+                       void* stream);
+#define TML_COMBINED_SERIES 18u /* 6 phases x {median, worst, sum} */
+/* series_dev[(phase*3 + k) * n_common + j]; rank_rows = device pointers to every
+ * present rank's aligned rows (local, gathered or peer-mapped), in rank order. */
+int tml_combined_series(tml_ctx* ctx, const void* const* rank_rows,
+                        uint32_t n_ranks, uint64_t n_common, double* series_dev,
+                        void* stream);
+
 /* ---------------------------------------------------------------- DIAGNOSIS
  * Host C++ rule engines (O(R) scalars).  Each writes one UTF-8 JSON object
  * whose keys mirror the reference's DiagnosticResult dataclasses. */

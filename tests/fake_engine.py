@@ -158,3 +158,69 @@ class FakeEngine:
             a.max_ratio = -1.0
             return a
         return _agg_from_records(self.procs, max_rows)
+
+    # ---- live tick (tml_combined_*): numpy double of csrc/tml_combined.cuh
+    def combined_prepare(self, lookback, stream=0):
+        r = self.records[-int(lookback):] if len(self.records) else self.records
+        n = len(r)
+        self.c_rows = np.zeros((n, 8))
+        self.c_rows[:, :6] = r["dur_ns"].astype(np.float64) / 1.0e6
+        self.c_rows[:, 6] = r["peak_alloc"].astype(np.float64)
+        self.c_rows[:, 7] = r["peak_resv"].astype(np.float64)
+        self.c_steps = r["step"].astype(np.int64)
+        last = np.ones(n, bool)
+        if n > 1:
+            last[:-1] = self.c_steps[1:] != self.c_steps[:-1]
+        self.c_cand = last
+        return SimpleNamespace(n_rows=n, n_cand=int(last.sum()),
+                               lo=int(self.c_steps[last].min()) if n else 0,
+                               hi=int(self.c_steps[last].max()) if n else 0,
+                               latest_step=int(self.c_steps.max()) if n else 0, monotone=1)
+
+    def combined_presence(self, glo, span, presence, stream=0):
+        if not self.c_cand.any():
+            presence.fill_(1)
+            return
+        presence.zero_()
+        self.c_rowof = np.full(span, -1, dtype=np.int64)
+        for i in np.nonzero(self.c_cand)[0]:
+            s = int(self.c_steps[i]) - glo
+            if 0 <= s < span:
+                presence[s] = 1
+                self.c_rowof[s] = i
+
+    def combined_select(self, glo, span, presence, window, stream=0):
+        idx = np.nonzero(presence.cpu().numpy())[0][-int(window):]
+        n = len(idx)
+        out = SimpleNamespace(n_common=n, n_rows=0, sums=[0.0] * 6)
+        self.c_x = None
+        if n == 0 or not self.c_cand.any():
+            return out
+        self.c_x = torch.from_numpy(np.ascontiguousarray(self.c_rows[self.c_rowof[idx]]))
+        self.c_sel_steps = [int(glo + i) for i in idx]
+        sums = [0.0] * 6
+        for row in self.c_x.numpy():  # ascending step order
+            for k in range(6):
+                sums[k] += float(row[k])
+        out.n_rows, out.sums = n, sums
+        return out
+
+    def combined_rows_tensor(self, n):
+        return self.c_x.reshape(-1) if self.c_x is not None else torch.empty(0, dtype=torch.float64)
+
+    def combined_steps(self, n, stream=0):
+        return list(self.c_sel_steps)
+
+    def combined_series(self, ptrs, n, series, stream=0):
+        import ctypes as C
+
+        rows = [np.ctypeslib.as_array((C.c_double * (n * 8)).from_address(int(p))).reshape(n, 8)
+                for p in ptrs]
+        out = series.numpy()
+        for m in range(6):
+            vals = np.stack([r[:, m] for r in rows], axis=1)  # [n, R]
+            for j in range(n):
+                v = np.ascontiguousarray(vals[j])
+                out[m * 3, j] = np.median(v)
+                out[m * 3 + 1, j] = np.max(v)
+                out[m * 3 + 2, j] = np.sum(v)

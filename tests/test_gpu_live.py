@@ -1,0 +1,130 @@
+"""GPU parity of the live tick (csrc/tml_combined.cuh + traceml_b200/live.py) through
+the C-ABI, against the reference's own StepCombinedComputer outputs
+(tests/golden/live) and the oracle.  Step ids, rank ids and status labels exact;
+floats rel <= 1e-9 (in practice bit-equal: the sums run in the reference's order)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import REL_TOL, assert_struct, plain
+
+pytestmark = pytest.mark.gpu
+
+LIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "live")
+CASES = json.load(open(os.path.join(LIVE, "INDEX.json")))["cases"]
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def _engines(records, ring_slots=None):
+    from traceml_b200.engine import Engine
+
+    R = len(records)
+    out = []
+    for r in range(R):
+        n = len(records[r])
+        e = Engine(device=0, rank=r, world=R, ring_slots=ring_slots or max(64, n + 16), proc_slots=64)
+        if n:
+            e.load_steps(records[r])
+        out.append(e)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_live_vs_reference_golden(cuda, name):
+    from traceml_b200 import replay
+    from traceml_b200.live import StepCombinedComputer
+
+    g = json.load(open(os.path.join(LIVE, name + ".json")))
+    recs = replay.make_step_replay(g["scenario"], g["ranks"], g["steps"], g["seed"])
+    assert replay.replay_digest(recs) == g["digest"]
+    engines = _engines(recs)
+    try:
+        comp = StepCombinedComputer(engines, window_size=g["window"])
+        with torch.cuda.stream(comp._stream):
+            cli = comp._compute_impl(include_series=True, include_rank_heatmap=False)
+            dash = comp._compute_impl(include_series=False, include_rank_heatmap=True)
+    finally:
+        for e in engines:
+            e.close()
+    assert cli["status_message"] == g["cli"]["status_message"]
+    assert_struct(plain(cli), g["cli"], name + ".cli", rel=REL_TOL)
+    assert_struct(plain(dash), g["dashboard"], name + ".dashboard", rel=REL_TOL)
+    # integer / label side and the rank order of the heat map: exact
+    for a, b in zip(cli["metrics"], g["cli"]["metrics"]):
+        assert a["summary"]["worst_rank"] == b["summary"]["worst_rank"]
+        if b["series"]:
+            assert a["series"]["steps"] == b["series"]["steps"]
+    if g["dashboard"]["rank_heatmap"]:
+        assert [r["rank"] for r in dash["rank_heatmap"]["rows"]] == \
+               [r["rank"] for r in g["dashboard"]["rank_heatmap"]["rows"]]
+
+
+def test_live_ring_wrap_and_oracle(cuda):
+    """The ring wrapped many times; the tick must see only the newest look-back rows."""
+    from oracle import live_oracle
+    from traceml_b200 import records as rec_mod
+    from traceml_b200 import replay
+    from traceml_b200.live import StepCombinedComputer
+
+    R, S, W = 4, 3000, 100
+    recs = replay.make_step_replay("ragged", R, S, 5)
+    engines = _engines(recs, ring_slots=1024)
+    try:
+        got = StepCombinedComputer(engines, window_size=W).compute_cli()
+    finally:
+        for e in engines:
+            e.close()
+    rows = {r: [rec_mod.step_record_to_wire(x, device=f"cuda:{r}") for x in recs[r]] for r in recs}
+    ref = live_oracle.live_step_time(rows, window=W)
+    assert_struct(plain(got), plain(ref), "wrap", rel=REL_TOL)
+
+
+def test_live_tick_during_training(cuda):
+    """A tick on its side stream while the step path keeps committing: it neither
+    waits for the training stream nor perturbs the committed records."""
+    import traceml_b200 as traceml
+    from traceml_b200 import runtime
+    from traceml_b200.live import StepCombinedComputer
+
+    from traceml_b200.runtime import reset_trace_session_state
+
+    reset_trace_session_state(0)
+    traceml.init(mode="auto")
+    eng = runtime.get_engine()
+    torch.cuda.synchronize()
+    eng.reset()
+    model = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 8)).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    comp = StepCombinedComputer([eng], window_size=16)
+    x = torch.randn(64, 256, device="cuda")
+    ticks = []
+    for i in range(60):
+        with traceml.trace_step(model):
+            loss = model(x).square().mean()
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        if i % 10 == 9:
+            ticks.append(comp.compute_cli())
+    torch.cuda.synchronize()
+    final = comp.compute_cli()
+    assert all(t["status_message"].startswith("OK") for t in ticks)
+    used = [t["metrics"][0]["summary"]["steps_used"] for t in ticks]
+    assert used[-1] == 16 and all(u <= 16 for u in used)
+    st = {m["metric"]: m for m in final["metrics"]}
+    assert st["step_time"]["series"]["steps"] == list(range(45, 61))
+    assert st["step_time"]["summary"]["median_total"] > 0.0
+    assert st["forward"]["summary"]["median_total"] > 0.0
+    assert np.isclose(sum(st["step_time"]["series"]["sum"]), st["step_time"]["summary"]["worst_total"],
+                      rtol=1e-12)

@@ -1233,7 +1233,10 @@ struct tml_ctx {
   u64* d_bandcnt = nullptr;
   void* h_stage = nullptr;       // pinned 4 KB result staging
   std::unordered_map<std::string, void*> peers;
+  void* comb = nullptr;          // live step-combined workspace (tml_combined.cuh)
 };
+
+static void comb_free(tml_ctx* c);
 
 static int grid_for(const tml_ctx* c, u64 work_items, int per_block) {
   u64 need = (work_items + per_block - 1) / per_block;
@@ -1313,6 +1316,7 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_winacc); cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
   cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
+  comb_free(c);
   delete c;
   return TML_OK;
 }
@@ -1973,3 +1977,5 @@ int tml_proc_reduce(tml_ctx* c, uint32_t max_rows, void* stream, tml_proc_agg* o
 }
 
 }  // extern "C"
+
+#include "tml_combined.cuh"
