@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--window", type=int, default=4_000_000, help="W: step records per rank")
     ap.add_argument("--sample", type=int, default=40_000, help="cpu-baseline rows per rank")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl", "a2a"])
     ap.add_argument("--no-overhead", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -435,6 +435,13 @@ def main():
         "k_window_rows": {"ms": med.get("k3a"), "bytes": k3a_bytes,
                           "GBps": k3a_bytes / (med["k3a"] * 1e-3) / 1e9 if med.get("k3a") else None},
     }
+    if R > 1 and med.get("k4"):
+        # step-sharded K4 loads (R-1)/R of its rows from peer HBM: NVLink 5 (900 GB/s per
+        # direction per GPU, B200_PROFILING.md) is its bound, not the local HBM
+        nv = (R - 1) * n_shard * 64.0
+        kernels["k_window_reduce"]["nvlink"] = {
+            "bytes_in": nv, "GBps": nv / (med["k4"] * 1e-3) / 1e9, "peak": 900.0,
+            "frac": nv / (med["k4"] * 1e-3) / 1e9 / 900.0}
     dom = max(kernels, key=lambda k: kernels[k]["ms"] or 0.0)
     traffic = None
     try:  # DRAM traffic per launch from the committed ncu capture, if it is this workload

@@ -112,7 +112,15 @@ class FakeEngine:
     # ---- stage 4
     def win_reduce(self, rows, mask, n, lo, hi, series, stream=0):
         R = len(rows)
-        a = np.stack([r.numpy().reshape(n, 8)[lo:hi] for r in rows])  # [R, m, 8]
+
+        def shard(r):
+            if isinstance(r, int):  # virtual base pointer (a2a exchange): rows lo..hi live at r + j*64
+                import ctypes as C
+                m = hi - lo
+                return np.ctypeslib.as_array((C.c_double * (m * 8)).from_address(r + lo * 64)).reshape(m, 8)
+            return r.numpy().reshape(n, 8)[lo:hi]
+
+        a = np.stack([shard(r) for r in rows])  # [R, m, 8]
         dl, fwd, bwd, opt, wall = a[..., 0], a[..., 2], a[..., 3], a[..., 4], a[..., 5]
         comp = (fwd + bwd) + opt
         traced = np.maximum(wall, comp)

@@ -4,8 +4,10 @@
         --master-port 29533 tests/multi_gpu_check.py
 
 Every rank loads ITS replay records, the job runs the cross-rank reduce with the
-fused NVLink peer-load exchange ("p2p") and with the NCCL all-gather exchange
-("nccl"); rank 0 checks both against the oracle (test infrastructure)."""
+fused NVLink peer-load exchange ("p2p"), the NCCL all-gather ("nccl") and the
+step-sharded NCCL all-to-all ("a2a"); rank 0 checks them against each other and
+the oracle (test infrastructure).  Then the live tick (StepCombined twin) runs
+across the real ranks and is checked against its oracle."""
 import os
 import sys
 
@@ -34,7 +36,7 @@ def main():
                 replay.make_step_replay(scenario, world, S, seed=11, only_ranks=[rank])[rank])
         procs = replay.make_proc_replay("overhang", world, 500, seed=11, only_ranks=[rank])[rank]
         results = {}
-        for mode in ("p2p", "nccl"):
+        for mode in ("p2p", "nccl", "a2a"):
             eng = Engine(device=local, rank=rank, world=world, ring_slots=max(64, len(mine) + 8), proc_slots=1024)
             if len(mine):
                 eng.load_steps(mine)
@@ -50,6 +52,9 @@ def main():
             try:
                 a, b = results["p2p"], results["nccl"]
                 assert_struct(plain(a["step_time"]), plain(b["step_time"]), f"{scenario}: p2p == nccl", rel=0.0)
+                c = results["a2a"]
+                assert_struct(plain(a["step_time"]), plain(c["step_time"]), f"{scenario}: p2p == a2a", rel=0.0)
+                assert_struct(plain(a["step_memory"]["diagnosis"]), plain(c["step_memory"]["diagnosis"]), "mem p2p == a2a", rel=0.0)
                 assert_struct(plain(a["step_memory"]["diagnosis"]), plain(b["step_memory"]["diagnosis"]), "mem p2p == nccl", rel=0.0)
                 if recs_all is not None:
                     ref = step_time_oracle.step_time_section(oracle_time_rows(recs_all, W), max_rows=W)
@@ -68,10 +73,45 @@ def main():
                     assert a["step_time"]["data"]["aligned_window"]["steps_analyzed"] == W
                 print(f"[multi_gpu_check] {scenario} R={world} W={W}: OK "
                       f"({a['step_time']['diagnosis']['primary']['status'] if a['step_time']['diagnosis'] else None}); "
-                      f"p2p {a['reduce'].timings_ms.get('total', 0):.3f} ms, nccl {b['reduce'].timings_ms.get('total', 0):.3f} ms")
+                      f"p2p {a['reduce'].timings_ms.get('total', 0):.3f} ms, nccl {b['reduce'].timings_ms.get('total', 0):.3f} ms, "
+                      f"a2a {c['reduce'].timings_ms.get('total', 0):.3f} ms")
             except AssertionError as exc:
                 failures += 1
                 print(f"[multi_gpu_check] {scenario}: FAILED {exc}")
+    # ---- live tick across the real ranks
+    from oracle import live_oracle
+    from traceml_b200 import records as rec_mod
+    from traceml_b200.live import StepCombinedComputer
+
+    for scenario, S, W in (("ragged", 700, 100), ("input_straggler", 460, 100), ("duplicates", 300, 64)):
+        recs_all = replay.make_step_replay(scenario, world, S, seed=13)
+        eng = Engine(device=local, rank=rank, world=world, ring_slots=max(64, len(recs_all[rank]) + 16),
+                     proc_slots=64)
+        if len(recs_all[rank]):
+            eng.load_steps(recs_all[rank])
+        torch.cuda.synchronize()
+        comp = StepCombinedComputer([eng], TorchDistComm(), window_size=W)
+        import time as _t
+        got = comp.compute_cli()
+        t0 = _t.perf_counter()
+        for _ in range(5):
+            got = comp.compute_cli()
+        tick_ms = (_t.perf_counter() - t0) / 5 * 1e3
+        dash = comp.compute_dashboard()
+        dist.barrier()
+        eng.close()
+        if rank == 0:
+            try:
+                rows = {r: [rec_mod.step_record_to_wire(x, device=f"cuda:{r}") for x in recs_all[r]]
+                        for r in recs_all}
+                assert_struct(plain(got), plain(live_oracle.live_step_time(rows, window=W)), "live.cli", rel=1e-9)
+                assert_struct(plain(dash), plain(live_oracle.live_step_time(
+                    rows, window=W, include_series=False, include_rank_heatmap=True)), "live.dash", rel=1e-9)
+                print(f"[multi_gpu_check] live {scenario} R={world} W={W}: OK ({got['status_message']}); "
+                      f"tick {tick_ms:.3f} ms")
+            except AssertionError as exc:
+                failures += 1
+                print(f"[multi_gpu_check] live {scenario}: FAILED {exc}")
     t = torch.tensor([failures], device="cuda")
     dist.broadcast(t, 0)
     dist.destroy_process_group()

@@ -34,8 +34,11 @@ def _worker(rank, world, scenario, S, W, init_file, out_dir, exchange):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("scenario,S,W", [("straggler", 300, 10_000), ("ragged", 260, 128)])
-def test_two_rank_reduce_matches_oracle(scenario, S, W):
+@pytest.mark.parametrize("scenario,S,W,exchange", [("straggler", 300, 10_000, "nccl"),
+                                                   ("ragged", 260, 128, "nccl"),
+                                                   ("straggler", 300, 10_000, "a2a"),
+                                                   ("ragged", 261, 77, "a2a")])
+def test_two_rank_reduce_matches_oracle(scenario, S, W, exchange):
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
     from helpers import (assert_struct, oracle_mem_rows, oracle_proc_rows, oracle_time_rows, plain,
                          strip_device)
@@ -44,7 +47,7 @@ def test_two_rank_reduce_matches_oracle(scenario, S, W):
     world = 2
     with tempfile.TemporaryDirectory() as td:
         init_file = os.path.join(td, "init")
-        mp.spawn(_worker, args=(world, scenario, S, W, init_file, td, "nccl"), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, scenario, S, W, init_file, td, exchange), nprocs=world, join=True)
         got = [torch.load(os.path.join(td, f"r{r}.pt"), weights_only=False) for r in range(world)]
     # every rank computed the identical summary
     assert_struct(plain(got[0]["step_time"]), plain(got[1]["step_time"]), "ranks agree", rel=0.0)

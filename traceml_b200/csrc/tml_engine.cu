@@ -590,9 +590,6 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
   }
 }
 
-__global__ void k_copy7(const double* __restrict__ src, double* __restrict__ dst) {
-  if (threadIdx.x < 7) dst[threadIdx.x] = src[threadIdx.x];
-}
 
 // ------------------------------------------------------------------ K3b: presence
 
@@ -1289,11 +1286,11 @@ int tml_init(int device, int rank, int world, uint32_t ring_slots, uint32_t proc
   CK(cudaHostGetDevicePointer((void**)&c->d_mirror, c->h_mirror, 0));
   CK(cudaHostAlloc(&c->h_pmirror, (size_t)c->pmirror_slots * sizeof(tml_proc_record), cudaHostAllocMapped));
   CK(cudaHostGetDevicePointer((void**)&c->d_pmirror, c->h_pmirror, 0));
-  CK(cudaMalloc(&c->d_winacc, sizeof(WinAcc)));
   CK(cudaMalloc(&c->d_total, sizeof(u64)));
   CK(cudaMalloc(&c->d_noncontig, sizeof(u32)));
   CK(cudaMalloc(&c->d_partials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
-  CK(cudaMalloc(&c->d_final, 64 * sizeof(double)));
+  CK(cudaMalloc(&c->d_final, 64 * sizeof(double) + sizeof(WinAcc)));
+  c->d_winacc = reinterpret_cast<WinAcc*>(c->d_final + 64);  // one D2H copy fetches both
   CK(cudaMalloc(&c->d_ppartials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
   CK(cudaMalloc(&c->d_pfinal, 32 * sizeof(double)));
   CK(cudaMalloc(&c->d_bandcnt, 64 * sizeof(u64)));
@@ -1313,7 +1310,7 @@ int tml_shutdown(tml_ctx* c) {
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_rowof[k]); cudaFree(c->d_xrows[k]); }
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
   cudaFree(c->d_noncontig);
-  cudaFree(c->d_winacc); cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
+  cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
   cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
   comb_free(c);
@@ -1580,20 +1577,21 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   CK(cudaEventRecord(c->ev1, s));
   k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
   CK(cudaPeekAtLastError());
-  k_copy7<<<1, 32, 0, s>>>(c->d_final + 32, c->d_final);
-  CK(cudaPeekAtLastError());
-  c->launches += 2;
-  if (n - c->win_tstart <= TML_EXACT_SUM_MAX) {  // reference-order sums (overwrite the tree sums)
+  c->launches += 2;  // K3a + its finalize
+  const bool exact_win = (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
+  if (exact_win) {  // reference-order sums (used instead of the tree sums)
     k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, c->d_flags, RF_USABLE | RF_IN_TIME, (long long)c->win_tstart,
                                 (long long)n - 1, 0, nullptr, nullptr, nullptr, -1ll, c->d_final);
     CK(cudaPeekAtLastError());
     c->launches += 1;
   }
+  // d_final[0..7) exact sums | d_final[32..43) tree sums + maxima | d_final[64..] WinAcc: one copy
   char* st = (char*)c->h_stage;
-  CK(cudaMemcpyAsync(st, c->d_winacc, sizeof(WinAcc), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(st + 256, c->d_final, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(st + 320, c->d_final + 32 + 7, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(st + 1024, c->d_final, 64 * sizeof(double) + sizeof(WinAcc), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  memcpy(st, st + 1024 + 64 * sizeof(double), sizeof(WinAcc));
+  memcpy(st + 256, st + 1024 + (exact_win ? 0 : 32) * sizeof(double), 7 * sizeof(double));
+  memcpy(st + 320, st + 1024 + (32 + 7) * sizeof(double), 4 * sizeof(double));
   WinAcc acc;
   memcpy(&acc, st, sizeof(acc));
   memcpy(out->t_sums, st + 256, 7 * sizeof(double));

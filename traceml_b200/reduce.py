@@ -60,6 +60,9 @@ class LocalComm:
     def all_gather_into(self, out: torch.Tensor, inp: torch.Tensor) -> None:
         out.copy_(inp)
 
+    def all_to_all(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits) -> None:
+        out.copy_(inp)
+
     def barrier(self) -> None:
         return None
 
@@ -102,6 +105,9 @@ class TorchDistComm:
 
     def all_gather_into(self, out: torch.Tensor, inp: torch.Tensor) -> None:
         self._dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def all_to_all(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits) -> None:
+        self._dist.all_to_all_single(out, inp, list(out_splits), list(in_splits), group=self.group)
 
     def barrier(self) -> None:
         self._dist.barrier(group=self.group)
@@ -193,6 +199,7 @@ class WindowReducer:
         self.L = len(self.engines)
         self.exchange = exchange
         self._series_cache: Dict[int, torch.Tensor] = {}
+        self._p2p_warm = False  # peer mappings already open: p2p costs nothing extra
         self._k4_events: List[Any] = []
 
     # global rank of local engine l
@@ -226,7 +233,9 @@ class WindowReducer:
                 "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20]), "dense": [i(v[21]), i(v[22])]}
 
     def reduce(self, window: int, *, want_series: bool = False,
-               proc_rows: Optional[int] = None) -> ReduceOutput:
+               proc_rows: Optional[int] = None, overlap=None) -> ReduceOutput:
+        """``overlap(proc_aggs)``: host work that needs only the process aggregates; it
+        runs after K4 has been launched and before the first wait on it."""
         window = max(1, int(window))
         dev = self.device
         stream = _stream_of(dev)
@@ -298,15 +307,21 @@ class WindowReducer:
         same = (t_res.n_common > 0 and t_res.n_common == m_res.n_common
                 and t_res.start_step == m_res.start_step and t_res.end_step == m_res.end_step
                 and t_res.used == m_res.used)
-        mode = self._exchange_mode()
+        mode = self._exchange_mode(t_res.n_common or m_res.n_common)
         if same:
             self._reduce_pass(KIND_TIME, _abi.MASK_TIME | _abi.MASK_MEM, t_res, stream, mode)
             m_res.series, m_res.shard = t_res.series, t_res.shard
         else:
             if t_res.n_common:
-                self._reduce_pass(KIND_TIME, _abi.MASK_TIME, t_res, stream, mode)
+                self._reduce_pass(KIND_TIME, _abi.MASK_TIME, t_res, stream,
+                                  self._exchange_mode(t_res.n_common))
             if m_res.n_common:
-                self._reduce_pass(KIND_MEM, _abi.MASK_MEM, m_res, stream, mode)
+                self._reduce_pass(KIND_MEM, _abi.MASK_MEM, m_res, stream,
+                                  self._exchange_mode(m_res.n_common))
+        if mode == "p2p":
+            self._p2p_warm = True
+        if overlap is not None:  # the GPU is busy with K4: free host time
+            overlap(proc_aggs)
         hw.append(_time.perf_counter())
         if ev:
             ev[3].record()
@@ -371,7 +386,7 @@ class WindowReducer:
         needs no collective of its own."""
         out = ([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
                + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
-        if self._exchange_mode() == "p2p":
+        if self._exchange_mode(int(a.n_common)) == "p2p":
             handle = engine.win_rows_export(kind) if int(a.n_rows) > 0 else bytes(72)
             out += [float(b) for b in handle]
         return out
@@ -379,7 +394,8 @@ class WindowReducer:
     def _collect_aligns(self, kind, res, flat, part, infos) -> KindResult:
         res.handles = {}
         gathered = []
-        p2p = self._exchange_mode() == "p2p"
+        # n_common is identical on every rank, so every rank packed the same layout
+        p2p = len(flat) == _ALIGN_LEN * self.L
         alen = _ALIGN_LEN if p2p else 15
         for row in self.comm.all_gather_vec(flat, self.device):
             lst = []
@@ -406,12 +422,24 @@ class WindowReducer:
         return res
 
     # ------------------------------------------------------------------ exchange
-    def _exchange_mode(self) -> str:
+    # One-shot cost of the fused peer-load exchange is the CUDA-IPC mapping of R-1 peer
+    # allocations (measured on 8 x B200: 44-65 ms the first time, 0 once cached), so it
+    # pays only for large or repeated windows.  Below this many aligned rows per rank the
+    # step-sharded NCCL all-to-all (2.7-7 ms one-shot at R = 8) is the default.
+    P2P_MIN_ROWS = 1_000_000
+
+    def _exchange_mode(self, n_common: Optional[int] = None) -> str:
         if self.comm.world == 1:
             return "local"
-        if self.exchange in ("p2p", "nccl"):
+        if self.exchange in ("p2p", "nccl", "a2a"):
+            if self.exchange == "a2a" and self.L != 1:
+                return "nccl"
             return self.exchange
-        return "p2p" if self.device.type == "cuda" else "nccl"
+        if self.device.type != "cuda":
+            return "nccl"
+        if n_common is not None and n_common < self.P2P_MIN_ROWS and not self._p2p_warm:
+            return "a2a" if self.L == 1 else "nccl"
+        return "p2p"
 
     def _reduce_pass(self, kind: int, mask: int, res: KindResult, stream, mode: str) -> None:
         n = res.n_common
@@ -439,6 +467,23 @@ class WindowReducer:
             for r in used:
                 rows[r] = gathered[r * n * 8:(r + 1) * n * 8]
             self._keep = gathered
+        elif mode == "a2a":
+            # step-sharded NCCL all-to-all: rank g receives only the rows of ITS shard of the
+            # steps from every rank ((R-1)/R * n * 64 B instead of (R-1) * n * 64 B), and K4
+            # reads them through virtual base pointers (row j of rank r sits at
+            # recv[r] + (j - shard_lo) * 64)
+            W = self.comm.world
+            g = self.comm.index
+            bounds = [(n * d) // W for d in range(W + 1)]
+            mine = (self.engines[0].win_rows_tensor(kind, n) if g in used
+                    else torch.zeros(n * 8, dtype=torch.float64, device=dev))
+            my_len = bounds[g + 1] - bounds[g]
+            recv = torch.empty(max(1, W * my_len * 8), dtype=torch.float64, device=dev)
+            self.comm.all_to_all(recv[:W * my_len * 8], mine, [my_len * 8] * W,
+                                 [(bounds[d + 1] - bounds[d]) * 8 for d in range(W)])
+            for r in used:
+                rows[r] = recv.data_ptr() + (r * my_len - bounds[g]) * 64
+            self._keep = recv
         else:
             # p2p: CUDA-IPC peer mappings, loads fused into the reduce kernel.  No barrier is
             # needed around it: (1) a rank's rows are complete before it enters the aligns

@@ -285,15 +285,23 @@ class SummaryEngine:
         import torch
 
         gpu_count = self.gpu_count if self.gpu_count is not None else torch.cuda.device_count()
-        out = self.reducer.reduce(window, proc_rows=max(1, int(proc_rows)))
-        aggs: Dict[int, Dict[str, Any]] = {}
-        for r, a in out.proc_aggs.items():
-            d = dict(a)
+        box: Dict[str, Any] = {}
+
+        def _process(proc_aggs):
             # ram_total / gpu_count are per-host constants (psutil.virtual_memory().total,
             # torch.cuda.device_count()); single-node scope: identical on every rank
-            d["ram_total"] = float(self.ram_total)
-            d["gpu_count"] = int(gpu_count)
-            aggs[r] = d
+            aggs: Dict[int, Dict[str, Any]] = {}
+            for r, a in proc_aggs.items():
+                d = dict(a)
+                d["ram_total"] = float(self.ram_total)
+                d["gpu_count"] = int(gpu_count)
+                aggs[r] = d
+            box["aggs"] = aggs
+            box["process"] = build_process(aggs)
+
+        # the process rules need only the first exchange: they run under the K4 launch
+        out = self.reducer.reduce(window, proc_rows=max(1, int(proc_rows)), overlap=_process)
+        aggs = box["aggs"]
         with_gpu = [a for a in aggs.values() if a["n_gpu"] > 0]
         gpu_total = max((a["max_total"] for a in with_gpu), default=None)
         saw = [a for a in aggs.values() if a["n"] > 0]
@@ -301,7 +309,7 @@ class SummaryEngine:
         return {
             "step_time": build_step_time(out),
             "step_memory": build_step_memory(out, gpu_total, no_gpu),
-            "process": build_process(aggs),
+            "process": box["process"],
             "reduce": out,
         }
 
