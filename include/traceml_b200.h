@@ -342,52 +342,64 @@ int tml_proc_reduce_launch(tml_ctx* ctx, uint32_t max_rows, void* stream);
 int tml_proc_reduce_collect(tml_ctx* ctx, tml_proc_agg* out);
 
 /* ---------------------------------------------------------------- LIVE TICK
- * The render-tick twin of the window reduce: what the reference's live CLI /
- * dashboard recompute every second from SQLite (StepCombinedComputer,
- * renderers/step_time/compute.py:129-315).  Same staging as the reduce above,
- * over the last `lookback = 4 x window` records (compute.py:366-368):
- *   prepare  -> rows of the look-back records; candidate = newest row of a step id
- *               (compute.py:371-401); bounds for the intersection
- *   presence -> bytes over [glo, glo+span); caller MIN-all-reduces them
- *   select   -> last `window` common step ids (compute.py:452-470), this rank's
- *               rows for them, and their six raw window sums in ascending step
- *               order (compute.py:502-531: dl, h2d, fwd, bwd, opt, step wall)
- *   series   -> per-step median / worst / sum across ranks (compute.py:573-596)
+ * The render-tick twins of the window reduce: what the reference's live CLI /
+ * dashboard recompute every second from SQLite.
+ *   kind TML_KIND_TIME  StepCombinedComputer._compute_impl
+ *                       (renderers/step_time/compute.py:129-315)
+ *   kind TML_KIND_MEM   build_step_memory_combined_result
+ *                       (renderers/step_memory/common.py:215-356)
+ * Same staging as the reduce above, over the newest `lookback` ring records:
+ *   prepare  -> 64-B rows; candidate = newest row of a step id (time:
+ *               compute.py:371-401) / newest row with non-NULL peaks (memory:
+ *               common.py:143-178); bounds for the intersection
+ *   presence -> bytes over [glo, glo+span); caller MIN-all-reduces them.  Memory
+ *               view: a rank with no candidate in range writes all ones -- the
+ *               reference drops it from the rank maps (common.py:262-275)
+ *   select   -> last `window` common step ids (compute.py:452-470,
+ *               common.py:359-397), this rank's rows for them, the six raw phase
+ *               sums in ascending step order (compute.py:502-531) and the two
+ *               memory peaks (common.py:289)
+ *   series   -> per-step median / worst / sum across ranks (compute.py:573-596,
+ *               common.py:286-287)
  * Runs on any stream, concurrently with the step path (the ring head is read on
  * the device; nothing here touches the training stream).                      */
 typedef struct tml_combined_info {
-  uint64_t n_rows;      /* look-back rows read from the ring                  */
-  uint64_t n_cand;      /* distinct step ids among them                       */
+  uint64_t n_rows;      /* look-back rows read from the ring (any row counts)  */
+  uint64_t n_cand;      /* candidate step ids among them                      */
   uint64_t lo, hi;      /* min / max candidate step id (valid if n_cand > 0)  */
   uint64_t latest_step; /* max step id: min over ranks = completed_step       */
+  uint64_t first_step;  /* step id of the oldest look-back row                */
+  uint32_t truncated;   /* 1: the ring holds older rows than the look-back    */
   uint32_t monotone;
-  uint32_t _pad;
 } tml_combined_info;
 
 typedef struct tml_combined_align {
   uint64_t n_common;    /* steps_used (<= window), identical on every rank    */
-  uint64_t n_rows;      /* this rank's rows for them (0 if it has no rows)    */
+  uint64_t n_rows;      /* this rank's rows for them (0: it is not in the
+                           window -- no rows, or no candidate in range)       */
   double sums[6];       /* dl, h2d, fwd, bwd, opt, step wall (ms)             */
+  double peaks[2];      /* max peak_alloc, max peak_resv over the window (B)  */
 } tml_combined_align;
 
-int tml_combined_prepare(tml_ctx* ctx, uint32_t lookback, void* stream,
-                         tml_combined_info* out);
-int tml_combined_presence(tml_ctx* ctx, uint64_t glo, uint64_t span,
-                          uint8_t* presence_dev, void* stream);
-int tml_combined_select(tml_ctx* ctx, uint64_t glo, uint64_t span,
+int tml_combined_prepare(tml_ctx* ctx, uint32_t kind, uint32_t lookback,
+                         void* stream, tml_combined_info* out);
+int tml_combined_presence(tml_ctx* ctx, uint32_t kind, uint64_t glo,
+                          uint64_t span, uint8_t* presence_dev, void* stream);
+int tml_combined_select(tml_ctx* ctx, uint32_t kind, uint64_t glo, uint64_t span,
                         const uint8_t* presence_dev, uint32_t window,
                         void* stream, tml_combined_align* out);
 /* this rank's aligned rows (n_common x 64 B, ascending step id), or NULL */
-const void* tml_combined_rows(tml_ctx* ctx);
-/* the n_common aligned step ids -> host buffer */
-int tml_combined_steps(tml_ctx* ctx, uint64_t* steps_host, uint64_t cap,
-                       void* stream);
-#define TML_COMBINED_SERIES 18u /* 6 phases x {median, worst, sum} */
-/* series_dev[(phase*3 + k) * n_common + j]; rank_rows = device pointers to every
- * present rank's aligned rows (local, gathered or peer-mapped), in rank order. */
+const void* tml_combined_rows(tml_ctx* ctx, uint32_t kind);
+/* the n_common aligned step ids -> host buffer (only on a rank with n_rows > 0) */
+int tml_combined_steps(tml_ctx* ctx, uint32_t kind, uint64_t* steps_host,
+                       uint64_t cap, void* stream);
+/* series_dev[(col*3 + k) * n_common + j], k = median, worst, sum, for row columns
+ * first_col .. first_col+n_cols (time: 0, 6; memory: 6, 2).  rank_rows = device
+ * pointers to every present rank's aligned rows (local, gathered or peer-mapped),
+ * in rank order. */
 int tml_combined_series(tml_ctx* ctx, const void* const* rank_rows,
-                        uint32_t n_ranks, uint64_t n_common, double* series_dev,
-                        void* stream);
+                        uint32_t n_ranks, uint64_t n_common, uint32_t first_col,
+                        uint32_t n_cols, double* series_dev, void* stream);
 
 /* ---------------------------------------------------------------- DIAGNOSIS
  * Host C++ rule engines (O(R) scalars).  Each writes one UTF-8 JSON object

@@ -186,3 +186,85 @@ def live_step_time(rows_by_rank, *, window: int = 100, lookback_factor: int = 4,
     if median_rank is not None:
         status += f" | overall_median_rank=r{median_rank}"
     return {"metrics": list(metrics.values()), "status_message": status, "rank_heatmap": heat}
+
+
+# --------------------------------------------------------------------------- step memory
+def live_step_memory(mem_rows_by_rank, *, window: int = 100, gpu_available: Optional[bool] = None,
+                     metric_keys: Sequence[str] = ("peak_allocated", "peak_reserved")):
+    """``build_step_memory_combined_result`` (renderers/step_memory/common.py:215-356).
+
+    ``mem_rows_by_rank[rank]`` = ``[(step, peak_alloc | None, peak_resv | None), ...]`` in
+    insertion order (id order).  ``device`` (a majority vote broken by Python set order,
+    ``common.py:400-408``) is not reproduced.
+    """
+    ws = max(1, int(window))
+    latest = {int(r): max(int(s) for s, _, _ in rows) for r, rows in mem_rows_by_rank.items() if len(rows)}
+    if not latest:  # common.py:235-239
+        return {"metrics": [], "status_message": "Waiting for first fully completed step across all ranks…"}
+    world_size = len(latest)
+    completed = min(latest.values())
+    scan_span = max(ws * 20, ws + 1)  # common.py:245
+    start = max(0, completed - scan_span + 1)
+    rows_in_window = sum(1 for rows in mem_rows_by_rank.values() for s, _, _ in rows
+                         if start <= int(s) <= completed)
+    out = []
+    for mi, key in enumerate(metric_keys):
+        col = {"peak_allocated": 1, "peak_reserved": 2}[key]
+        rank_maps: Dict[int, Dict[int, float]] = {}
+        for r in sorted(mem_rows_by_rank):  # common.py:143-178: step DESC, id DESC, first wins
+            rows = mem_rows_by_rank[r]
+            cand = [(int(row[0]), i, row[col]) for i, row in enumerate(rows)
+                    if row[col] is not None and start <= int(row[0]) <= completed]
+            cand.sort(key=lambda t: (t[0], t[1]), reverse=True)
+            m: Dict[int, float] = {}
+            for s, _, v in cand:
+                if len(m) >= scan_span:
+                    break
+                if s in m:
+                    continue
+                m[s] = float(v)
+            if m:
+                rank_maps[int(r)] = m
+        if not rank_maps:
+            continue
+        maps = list(rank_maps.values())
+        steps_rev: List[int] = []  # common.py:359-397
+        step, scanned = int(completed), 0
+        while step >= 0 and len(steps_rev) < ws:
+            scanned += 1
+            if scanned > scan_span:
+                break
+            if all(step in m for m in maps):
+                steps_rev.append(step)
+            step -= 1
+        if not steps_rev:
+            continue
+        steps = steps_rev[::-1]
+        ranks_list = sorted(rank_maps)
+        values = np.array([[rank_maps[r][s] for s in steps] for r in ranks_list], dtype=np.float64)
+        median_arr = np.median(values, axis=0)
+        worst_arr = np.max(values, axis=0)
+        peaks = np.max(values, axis=1)
+        median_peak = float(np.median(peaks))
+        worst_peak = float(np.max(peaks))
+        worst_rank = int(ranks_list[int(np.argmax(peaks))])
+        skew_ratio = (worst_peak / median_peak) if median_peak > 0.0 else 0.0
+        skew_pct = ((worst_peak - median_peak) / median_peak) if median_peak > 0.0 else 0.0
+        out.append({
+            "metric": str(key),
+            "series": {"steps": [int(s) for s in steps], "median": median_arr.astype(float).tolist(),
+                       "worst": worst_arr.astype(float).tolist()},
+            "summary": {"window_size": ws, "steps_used": len(steps), "median_peak": median_peak,
+                        "worst_peak": worst_peak, "worst_rank": worst_rank,
+                        "skew_ratio": float(skew_ratio), "skew_pct": float(skew_pct)},
+            "coverage": {"expected_steps": ws, "steps_used": len(steps), "completed_step": int(completed),
+                         "world_size": int(world_size), "ranks_present": len(ranks_list),
+                         "incomplete": len(ranks_list) < world_size},
+        })
+    if out:
+        status = "OK"
+    elif gpu_available is False and rows_in_window > 0:
+        status = "No GPU detected. Step memory uses torch-based GPU memory telemetry."
+    else:
+        status = "No complete memory metrics available"
+    return {"metrics": out, "status_message": status}

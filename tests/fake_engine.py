@@ -17,7 +17,8 @@ RF_USABLE, RF_HAS_MEM, RF_IN_TIME, RF_CAND_T, RF_CAND_M = 1, 2, 4, 8, 16
 
 
 class FakeEngine:
-    def __init__(self, records, procs=None, device=0):
+    def __init__(self, records, procs=None, device=0, dense_ok=False):
+        self.dense_ok = dense_ok
         self.records = records
         self.procs = procs
         self.device = device
@@ -63,7 +64,22 @@ class FakeEngine:
             lo=[int(self.steps[self.cand[k]].min()) if self.cand[k].any() else 0 for k in (0, 1)],
             hi=[int(self.steps[self.cand[k]].max()) if self.cand[k].any() else 0 for k in (0, 1)],
             t_sums=sums, t_count=int(sel.sum()), n_both=int((self.cand[0] & self.cand[1]).sum()), dense=(0, 0))
+        if self.dense_ok:
+            rows_in = (n - self.t_start, n)
+            out.dense = tuple(int(out.n_cand[k] > 0 and out.n_cand[k] == rows_in[k]
+                                  and out.hi[k] - out.lo[k] + 1 == out.n_cand[k]) for k in (0, 1))
+        self.lo = out.lo
         return out
+
+    def win_select_dense(self, kind, first, n_common, stream=0):
+        """Dense window: row(step) = first_row + (step - lo); same outputs as win_select."""
+        span = int(n_common)
+        presence = torch.ones(span, dtype=torch.uint8)
+        rowof = (self.t_start if kind == 0 else 0) + (int(first) - self.lo[kind]) + np.arange(span)
+        if not hasattr(self, "rowof"):
+            self.rowof = {}
+        self.rowof[kind] = rowof
+        return self.win_select(kind, int(first), span, presence, span, stream)
 
     # ---- stage 2
     def win_presence(self, kind, glo, span, presence, stream=0):
@@ -168,65 +184,84 @@ class FakeEngine:
         return _agg_from_records(self.procs, max_rows)
 
     # ---- live tick (tml_combined_*): numpy double of csrc/tml_combined.cuh
-    def combined_prepare(self, lookback, stream=0):
-        r = self.records[-int(lookback):] if len(self.records) else self.records
+    def combined_prepare(self, kind, lookback, stream=0):
+        total = len(self.records)
+        r = self.records[-int(lookback):] if total else self.records
         n = len(r)
-        self.c_rows = np.zeros((n, 8))
-        self.c_rows[:, :6] = r["dur_ns"].astype(np.float64) / 1.0e6
-        self.c_rows[:, 6] = r["peak_alloc"].astype(np.float64)
-        self.c_rows[:, 7] = r["peak_resv"].astype(np.float64)
-        self.c_steps = r["step"].astype(np.int64)
+        c = SimpleNamespace()
+        c.rows = np.zeros((n, 8))
+        c.rows[:, :6] = r["dur_ns"].astype(np.float64) / 1.0e6
+        c.rows[:, 6] = r["peak_alloc"].astype(np.float64)
+        c.rows[:, 7] = r["peak_resv"].astype(np.float64)
+        c.steps = r["step"].astype(np.int64)
+        has_mem = (r["flags"] & 1) != 0
         last = np.ones(n, bool)
         if n > 1:
-            last[:-1] = self.c_steps[1:] != self.c_steps[:-1]
-        self.c_cand = last
+            last[:-1] = c.steps[1:] != c.steps[:-1]
+            if kind == 1:
+                last[:-1] |= ~has_mem[1:]
+        if kind == 1:
+            last &= has_mem
+        c.cand, c.n, c.inrange = last, n, 0
+        if not hasattr(self, "comb"):
+            self.comb = {}
+        self.comb[kind] = c
         return SimpleNamespace(n_rows=n, n_cand=int(last.sum()),
-                               lo=int(self.c_steps[last].min()) if n else 0,
-                               hi=int(self.c_steps[last].max()) if n else 0,
-                               latest_step=int(self.c_steps.max()) if n else 0, monotone=1)
+                               lo=int(c.steps[last].min()) if last.any() else 0,
+                               hi=int(c.steps[last].max()) if last.any() else 0,
+                               latest_step=int(c.steps.max()) if n else 0,
+                               first_step=int(c.steps[0]) if n else 0,
+                               truncated=int(total > n), monotone=1)
 
-    def combined_presence(self, glo, span, presence, stream=0):
-        if not self.c_cand.any():
+    def combined_presence(self, kind, glo, span, presence, stream=0):
+        c = self.comb[kind]
+        if c.n == 0:
+            presence.fill_(1)
+            return
+        inr = [i for i in np.nonzero(c.cand)[0] if 0 <= int(c.steps[i]) - glo < span]
+        c.inrange = len(inr)
+        if not inr and kind == 1:
             presence.fill_(1)
             return
         presence.zero_()
-        self.c_rowof = np.full(span, -1, dtype=np.int64)
-        for i in np.nonzero(self.c_cand)[0]:
-            s = int(self.c_steps[i]) - glo
-            if 0 <= s < span:
-                presence[s] = 1
-                self.c_rowof[s] = i
+        c.rowof = np.full(span, -1, dtype=np.int64)
+        for i in inr:
+            presence[int(c.steps[i]) - glo] = 1
+            c.rowof[int(c.steps[i]) - glo] = i
 
-    def combined_select(self, glo, span, presence, window, stream=0):
+    def combined_select(self, kind, glo, span, presence, window, stream=0):
+        c = self.comb[kind]
         idx = np.nonzero(presence.cpu().numpy())[0][-int(window):]
         n = len(idx)
-        out = SimpleNamespace(n_common=n, n_rows=0, sums=[0.0] * 6)
-        self.c_x = None
-        if n == 0 or not self.c_cand.any():
+        out = SimpleNamespace(n_common=n, n_rows=0, sums=[0.0] * 6, peaks=[0.0, 0.0])
+        c.x = None
+        if n == 0 or c.n == 0 or c.inrange == 0:
             return out
-        self.c_x = torch.from_numpy(np.ascontiguousarray(self.c_rows[self.c_rowof[idx]]))
-        self.c_sel_steps = [int(glo + i) for i in idx]
+        c.x = torch.from_numpy(np.ascontiguousarray(c.rows[c.rowof[idx]]))
+        c.sel_steps = [int(glo + i) for i in idx]
         sums = [0.0] * 6
-        for row in self.c_x.numpy():  # ascending step order
+        for row in c.x.numpy():  # ascending step order
             for k in range(6):
                 sums[k] += float(row[k])
         out.n_rows, out.sums = n, sums
+        out.peaks = [float(c.x[:, 6].max()), float(c.x[:, 7].max())]
         return out
 
-    def combined_rows_tensor(self, n):
-        return self.c_x.reshape(-1) if self.c_x is not None else torch.empty(0, dtype=torch.float64)
+    def combined_rows_tensor(self, kind, n):
+        c = self.comb[kind]
+        return c.x.reshape(-1) if c.x is not None else torch.empty(0, dtype=torch.float64)
 
-    def combined_steps(self, n, stream=0):
-        return list(self.c_sel_steps)
+    def combined_steps(self, kind, n, stream=0):
+        return list(self.comb[kind].sel_steps)
 
-    def combined_series(self, ptrs, n, series, stream=0):
+    def combined_series(self, ptrs, n, first_col, n_cols, series, stream=0):
         import ctypes as C
 
         rows = [np.ctypeslib.as_array((C.c_double * (n * 8)).from_address(int(p))).reshape(n, 8)
                 for p in ptrs]
         out = series.numpy()
-        for m in range(6):
-            vals = np.stack([r[:, m] for r in rows], axis=1)  # [n, R]
+        for m in range(n_cols):
+            vals = np.stack([r[:, first_col + m] for r in rows], axis=1)  # [n, R]
             for j in range(n):
                 v = np.ascontiguousarray(vals[j])
                 out[m * 3, j] = np.median(v)

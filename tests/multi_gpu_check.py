@@ -81,7 +81,7 @@ def main():
     # ---- live tick across the real ranks
     from oracle import live_oracle
     from traceml_b200 import records as rec_mod
-    from traceml_b200.live import StepCombinedComputer
+    from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
 
     for scenario, S, W in (("ragged", 700, 100), ("input_straggler", 460, 100), ("duplicates", 300, 64)):
         recs_all = replay.make_step_replay(scenario, world, S, seed=13)
@@ -98,6 +98,7 @@ def main():
             got = comp.compute_cli()
         tick_ms = (_t.perf_counter() - t0) / 5 * 1e3
         dash = comp.compute_dashboard()
+        mem = StepMemoryCombinedComputer([eng], TorchDistComm(), window_size=W).compute()
         dist.barrier()
         eng.close()
         if rank == 0:
@@ -107,6 +108,13 @@ def main():
                 assert_struct(plain(got), plain(live_oracle.live_step_time(rows, window=W)), "live.cli", rel=1e-9)
                 assert_struct(plain(dash), plain(live_oracle.live_step_time(
                     rows, window=W, include_series=False, include_rank_heatmap=True)), "live.dash", rel=1e-9)
+                mrows = {r: [(int(s_), float(a_), float(v_)) for s_, a_, v_ in
+                             zip(recs_all[r]["step"], recs_all[r]["peak_alloc"], recs_all[r]["peak_resv"])]
+                         for r in recs_all}
+                for m in mem["metrics"]:
+                    m.pop("device", None)
+                assert_struct(plain(mem), plain(live_oracle.live_step_memory(mrows, window=W, gpu_available=True)),
+                              "live.mem", rel=1e-9)
                 print(f"[multi_gpu_check] live {scenario} R={world} W={W}: OK ({got['status_message']}); "
                       f"tick {tick_ms:.3f} ms")
             except AssertionError as exc:

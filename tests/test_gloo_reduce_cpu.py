@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, scenario, S, W, init_file, out_dir, exchange):
+def _worker(rank, world, scenario, S, W, init_file, out_dir, exchange, dense=False):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
@@ -24,12 +24,13 @@ def _worker(rank, world, scenario, S, W, init_file, out_dir, exchange):
 
     recs = replay.make_step_replay(scenario, world, S, seed=3)
     procs = replay.make_proc_replay("overhang", world, 200, seed=3)
-    eng = FakeEngine(recs[rank], procs[rank])
+    eng = FakeEngine(recs[rank], procs[rank], dense_ok=dense)
     se = sections.SummaryEngine([eng], TorchDistComm(), exchange=exchange,
                                 ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world)
     se.reducer.device = torch.device("cpu")
     res = se.build(W, W)
-    res.pop("reduce")
+    red = res.pop("reduce")
+    res["_exchanges"] = getattr(se.comm, "n_vec", None)
     torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
@@ -37,8 +38,12 @@ def _worker(rank, world, scenario, S, W, init_file, out_dir, exchange):
 @pytest.mark.parametrize("scenario,S,W,exchange", [("straggler", 300, 10_000, "nccl"),
                                                    ("ragged", 260, 128, "nccl"),
                                                    ("straggler", 300, 10_000, "a2a"),
-                                                   ("ragged", 261, 77, "a2a")])
+                                                   ("ragged", 261, 77, "a2a"),
+                                                   ("straggler", 300, 10_000, "dense"),
+                                                   ("straggler", 300, 128, "dense")])
 def test_two_rank_reduce_matches_oracle(scenario, S, W, exchange):
+    """"dense": the engine double reports dense windows, so the lock-step speculation
+    (alignment riding in the first exchange) and the dense select path are exercised."""
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
     from helpers import (assert_struct, oracle_mem_rows, oracle_proc_rows, oracle_time_rows, plain,
                          strip_device)
@@ -47,8 +52,16 @@ def test_two_rank_reduce_matches_oracle(scenario, S, W, exchange):
     world = 2
     with tempfile.TemporaryDirectory() as td:
         init_file = os.path.join(td, "init")
-        mp.spawn(_worker, args=(world, scenario, S, W, init_file, td, exchange), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, scenario, S, W, init_file, td, "nccl" if exchange == "dense" else exchange,
+                                exchange == "dense"), nprocs=world, join=True)
         got = [torch.load(os.path.join(td, f"r{r}.pt"), weights_only=False) for r in range(world)]
+    # exchanges per reduce: bounds(+speculative alignment), [alignment], bands
+    if scenario == "straggler":  # lock step; "ragged" aligns time and memory separately
+        # W < retained rows: memory candidates outnumber the time window -> its own alignment
+        want = 3 if exchange != "dense" else (2 if W >= S else 3)
+        assert got[0]["_exchanges"] == want, got[0]["_exchanges"]
+    for g_ in got:
+        g_.pop("_exchanges")
     # every rank computed the identical summary
     assert_struct(plain(got[0]["step_time"]), plain(got[1]["step_time"]), "ranks agree", rel=0.0)
     recs = replay.make_step_replay(scenario, world, S, seed=3)

@@ -128,3 +128,61 @@ def test_live_tick_during_training(cuda):
     assert st["forward"]["summary"]["median_total"] > 0.0
     assert np.isclose(sum(st["step_time"]["series"]["sum"]), st["step_time"]["summary"]["worst_total"],
                       rtol=1e-12)
+
+
+MEM_CASES = json.load(open(os.path.join(LIVE, "INDEX.json")))["mem_cases"]
+
+
+def _strip_dev(res):
+    for m in res["metrics"]:
+        m.pop("device", None)
+    return res
+
+
+@pytest.mark.parametrize("name", MEM_CASES)
+def test_live_memory_vs_reference_golden(cuda, name):
+    from traceml_b200 import replay
+    from traceml_b200.live import StepMemoryCombinedComputer
+
+    g = json.load(open(os.path.join(LIVE, name + ".json")))
+    recs = replay.make_step_replay(g["scenario"], g["ranks"], g["steps"], g["seed"])
+    assert replay.replay_digest(recs) == g["digest"]
+    engines = _engines(recs)
+    try:
+        comp = StepMemoryCombinedComputer(engines, window_size=g["window"], gpu_available=g["gpu_available"])
+        with torch.cuda.stream(comp._stream):
+            got = _strip_dev(comp._compute_impl())
+    finally:
+        for e in engines:
+            e.close()
+    assert got["status_message"] == g["result"]["status_message"]
+    assert_struct(plain(got), g["result"], name, rel=REL_TOL)
+    for a, b in zip(got["metrics"], g["result"]["metrics"]):
+        assert a["summary"]["worst_rank"] == b["summary"]["worst_rank"]
+        assert a["series"]["steps"] == b["series"]["steps"]
+        assert a["series"]["median"] == b["series"]["median"]  # bytes: exact
+        assert a["series"]["worst"] == b["series"]["worst"]
+
+
+def test_live_memory_far_ahead_rank(cuda):
+    """A rank thousands of steps ahead of the slowest: its in-range rows lie beyond the first
+    look-back and the ring has wrapped; the tick widens locally and stays exact."""
+    from oracle import live_oracle
+    from traceml_b200 import replay
+    from traceml_b200.live import StepMemoryMetricsComputer
+
+    recs = replay.make_step_replay("balanced", 2, 6000, 3)
+    recs[1] = recs[1][:900]
+    engines = _engines(recs, ring_slots=8192)
+    try:
+        got = _strip_dev(StepMemoryMetricsComputer(engines, cli_window_size=100).compute_cli())
+    finally:
+        for e in engines:
+            e.close()
+    rows = {}
+    for r in recs:
+        rows[r] = [(int(s), float(a), float(v)) for s, a, v in
+                   zip(recs[r]["step"], recs[r]["peak_alloc"], recs[r]["peak_resv"])]
+    ref = live_oracle.live_step_memory(rows, window=100, gpu_available=True)
+    assert ref["metrics"][0]["coverage"]["ranks_present"] == 2
+    assert_struct(plain(got), plain(ref), "far_ahead", rel=REL_TOL)

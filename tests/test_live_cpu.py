@@ -15,6 +15,23 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIVE = os.path.join(HERE, "golden", "live")
 CASES = json.load(open(os.path.join(LIVE, "INDEX.json")))["cases"]
+MEM_CASES = json.load(open(os.path.join(LIVE, "INDEX.json")))["mem_cases"]
+
+
+def mem_rows(records):
+    out = {}
+    for r in records:
+        has = (records[r]["flags"] & 1) != 0
+        out[r] = [(int(s), (float(a) if h else None), (float(v) if h else None))
+                  for s, a, v, h in zip(records[r]["step"], records[r]["peak_alloc"],
+                                        records[r]["peak_resv"], has)]
+    return out
+
+
+def strip_dev(res):
+    for m in res["metrics"]:
+        m.pop("device", None)
+    return res
 
 
 def load(name):
@@ -63,6 +80,46 @@ def test_live_host_logic_with_engine_double(name):
     assert_struct(plain(dash), g["dashboard"], name + ".dashboard", rel=0.0)
 
 
+@pytest.mark.parametrize("name", MEM_CASES)
+def test_live_memory_oracle_and_host_logic(name):
+    """Step-memory panel: oracle == reference golden, and live.py over the engine double
+    (all ranks local) == reference golden."""
+    from fake_engine import FakeEngine
+    from helpers import assert_struct, plain
+    from oracle import live_oracle
+    from traceml_b200 import replay
+    from traceml_b200.live import StepMemoryCombinedComputer
+
+    g = load(name)
+    recs = replay.make_step_replay(g["scenario"], g["ranks"], g["steps"], g["seed"])
+    assert replay.replay_digest(recs) == g["digest"]
+    o = live_oracle.live_step_memory(mem_rows(recs), window=g["window"], gpu_available=g["gpu_available"])
+    assert_struct(plain(o), g["result"], name + ".oracle", rel=0.0)
+    engines = [FakeEngine(recs[r]) for r in sorted(recs)]
+    comp = StepMemoryCombinedComputer(engines, window_size=g["window"], gpu_available=g["gpu_available"],
+                                      device=torch.device("cpu"))
+    got = strip_dev(comp._compute_impl())
+    assert_struct(plain(got), g["result"], name + ".host", rel=0.0)
+
+
+def test_live_memory_far_ahead_rank_widens_lookback():
+    """One rank thousands of steps ahead: its in-range rows lie beyond the first look-back."""
+    from fake_engine import FakeEngine
+    from helpers import assert_struct, plain
+    from oracle import live_oracle
+    from traceml_b200 import replay
+    from traceml_b200.live import StepMemoryCombinedComputer
+
+    recs = replay.make_step_replay("balanced", 2, 6000, 3)
+    recs[1] = recs[1][:900]  # rank 1 lags: completed = 900, window 801..900 far behind rank 0's tail
+    engines = [FakeEngine(recs[r]) for r in sorted(recs)]
+    comp = StepMemoryCombinedComputer(engines, window_size=100, gpu_available=True, device=torch.device("cpu"))
+    got = strip_dev(comp._compute_impl())
+    ref = live_oracle.live_step_memory(mem_rows(recs), window=100, gpu_available=True)
+    assert ref["metrics"] and ref["metrics"][0]["coverage"]["ranks_present"] == 2
+    assert_struct(plain(got), plain(ref), "widen", rel=0.0)
+
+
 def test_live_stale_handling():
     """compute.py:103-123, 424-446: an empty tick serves the last good result."""
     from fake_engine import FakeEngine
@@ -106,6 +163,39 @@ def _worker(rank, world, name, init_file, out_dir):
            "dashboard": comp._compute_impl(include_series=False, include_rank_heatmap=True)}
     torch.save(out, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
+
+
+def _mem_worker(rank, world, name, init_file, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    from fake_engine import FakeEngine
+    from traceml_b200 import replay
+    from traceml_b200.live import StepMemoryCombinedComputer
+    from traceml_b200.reduce import TorchDistComm
+
+    g = load(name)
+    recs = replay.make_step_replay(g["scenario"], g["ranks"], g["steps"], g["seed"])
+    L = g["ranks"] // world
+    engines = [FakeEngine(recs[rank * L + l]) for l in range(L)]
+    comp = StepMemoryCombinedComputer(engines, TorchDistComm(), window_size=g["window"],
+                                      gpu_available=g["gpu_available"], device=torch.device("cpu"))
+    torch.save(strip_dev(comp._compute_impl()), os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["livemem_ragged_r4", "livemem_no_overlap_r2", "livemem_default_r8"])
+def test_live_memory_two_process_gloo(name):
+    from helpers import assert_struct, plain
+
+    g = load(name)
+    world = 2
+    with tempfile.TemporaryDirectory() as td:
+        init_file = os.path.join(td, "init")
+        mp.spawn(_mem_worker, args=(world, name, init_file, td), nprocs=world, join=True)
+        got = [torch.load(os.path.join(td, f"r{r}.pt"), weights_only=False) for r in range(world)]
+    for r in range(world):
+        assert_struct(plain(got[r]), g["result"], f"{name}.r{r}", rel=0.0)
 
 
 @pytest.mark.parametrize("name", ["live_ragged_r4", "live_duplicates_r2", "live_wait_heavy_r8"])

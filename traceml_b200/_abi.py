@@ -60,11 +60,11 @@ class AlignInfo(C.Structure):
 
 class CombinedInfo(C.Structure):
     _fields_ = [("n_rows", u64), ("n_cand", u64), ("lo", u64), ("hi", u64), ("latest_step", u64),
-                ("monotone", u32), ("_pad", u32)]
+                ("first_step", u64), ("truncated", u32), ("monotone", u32)]
 
 
 class CombinedAlign(C.Structure):
-    _fields_ = [("n_common", u64), ("n_rows", u64), ("sums", f64 * 6)]
+    _fields_ = [("n_common", u64), ("n_rows", u64), ("sums", f64 * 6), ("peaks", f64 * 2)]
 
 
 class ReduceArgs(C.Structure):
@@ -155,12 +155,12 @@ SIGNATURES = {
     "tml_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "tml_peer_close": (C.c_int, [vp, vp]),
     "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),
-    "tml_combined_prepare": (C.c_int, [vp, u32, vp, C.POINTER(CombinedInfo)]),
-    "tml_combined_presence": (C.c_int, [vp, u64, u64, vp, vp]),
-    "tml_combined_select": (C.c_int, [vp, u64, u64, vp, u32, vp, C.POINTER(CombinedAlign)]),
-    "tml_combined_rows": (vp, [vp]),
-    "tml_combined_steps": (C.c_int, [vp, C.POINTER(u64), u64, vp]),
-    "tml_combined_series": (C.c_int, [vp, C.POINTER(vp), u32, u64, vp, vp]),
+    "tml_combined_prepare": (C.c_int, [vp, u32, u32, vp, C.POINTER(CombinedInfo)]),
+    "tml_combined_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
+    "tml_combined_select": (C.c_int, [vp, u32, u64, u64, vp, u32, vp, C.POINTER(CombinedAlign)]),
+    "tml_combined_rows": (vp, [vp, u32]),
+    "tml_combined_steps": (C.c_int, [vp, u32, C.POINTER(u64), u64, vp]),
+    "tml_combined_series": (C.c_int, [vp, C.POINTER(vp), u32, u64, u32, u32, vp, vp]),
     "tml_win_bands": (C.c_int, [vp, vp, C.POINTER(BandArgs), vp, C.POINTER(BandOut)]),
     "tml_proc_reduce": (C.c_int, [vp, u32, vp, C.POINTER(ProcAgg)]),
     "tml_proc_reduce_launch": (C.c_int, [vp, u32, vp]),

@@ -1230,7 +1230,7 @@ struct tml_ctx {
   u64* d_bandcnt = nullptr;
   void* h_stage = nullptr;       // pinned 4 KB result staging
   std::unordered_map<std::string, void*> peers;
-  void* comb = nullptr;          // live step-combined workspace (tml_combined.cuh)
+  void* comb[2] = {nullptr, nullptr};  // live step-combined workspaces, per kind (tml_combined.cuh)
 };
 
 static void comb_free(tml_ctx* c);

@@ -204,44 +204,46 @@ class Engine:
         _abi.check(self._lib.tml_peer_open(self._h, handle[:64], C.byref(p)), "tml_peer_open")
         return int(p.value) + int.from_bytes(handle[64:72], "little")
 
-    # ---- live tick (StepCombined twin): include/traceml_b200.h "LIVE TICK"
-    def combined_prepare(self, lookback: int, stream: int = 0) -> _abi.CombinedInfo:
+    # ---- live tick (StepCombined / step-memory combined twins): header "LIVE TICK"
+    def combined_prepare(self, kind: int, lookback: int, stream: int = 0) -> _abi.CombinedInfo:
         out = _abi.CombinedInfo()
-        _abi.check(self._lib.tml_combined_prepare(self._h, int(lookback), stream, C.byref(out)),
+        _abi.check(self._lib.tml_combined_prepare(self._h, kind, int(lookback), stream, C.byref(out)),
                    "tml_combined_prepare")
         return out
 
-    def combined_presence(self, glo: int, span: int, presence, stream: int = 0) -> None:
-        _abi.check(self._lib.tml_combined_presence(self._h, int(glo), int(span), _p(presence), stream),
-                   "tml_combined_presence")
+    def combined_presence(self, kind: int, glo: int, span: int, presence, stream: int = 0) -> None:
+        _abi.check(self._lib.tml_combined_presence(self._h, kind, int(glo), int(span), _p(presence),
+                                                   stream), "tml_combined_presence")
 
-    def combined_select(self, glo: int, span: int, presence, window: int,
+    def combined_select(self, kind: int, glo: int, span: int, presence, window: int,
                         stream: int = 0) -> _abi.CombinedAlign:
         out = _abi.CombinedAlign()
-        _abi.check(self._lib.tml_combined_select(self._h, int(glo), int(span), _p(presence), int(window),
-                                                 stream, C.byref(out)), "tml_combined_select")
+        _abi.check(self._lib.tml_combined_select(self._h, kind, int(glo), int(span), _p(presence),
+                                                 int(window), stream, C.byref(out)), "tml_combined_select")
         return out
 
-    def combined_rows_ptr(self) -> int:
-        return int(self._lib.tml_combined_rows(self._h) or 0)
+    def combined_rows_ptr(self, kind: int) -> int:
+        return int(self._lib.tml_combined_rows(self._h, kind) or 0)
 
-    def combined_rows_tensor(self, n_common: int):
+    def combined_rows_tensor(self, kind: int, n_common: int):
         import torch
 
-        ptr = self.combined_rows_ptr()
+        ptr = self.combined_rows_ptr(kind)
         if not ptr or n_common <= 0:
             return torch.empty(0, dtype=torch.float64, device=f"cuda:{self.device}")
         return torch.as_tensor(_DevView(ptr, n_common * 8), device=f"cuda:{self.device}")
 
-    def combined_steps(self, n_common: int, stream: int = 0):
+    def combined_steps(self, kind: int, n_common: int, stream: int = 0):
         buf = (C.c_uint64 * max(1, int(n_common)))()
-        _abi.check(self._lib.tml_combined_steps(self._h, buf, int(n_common), stream), "tml_combined_steps")
+        _abi.check(self._lib.tml_combined_steps(self._h, kind, buf, int(n_common), stream),
+                   "tml_combined_steps")
         return [int(buf[i]) for i in range(int(n_common))]
 
-    def combined_series(self, row_ptrs, n_common: int, series, stream: int = 0) -> None:
+    def combined_series(self, row_ptrs, n_common: int, first_col: int, n_cols: int, series,
+                        stream: int = 0) -> None:
         arr = (C.c_void_p * len(row_ptrs))(*[int(p) for p in row_ptrs])
-        _abi.check(self._lib.tml_combined_series(self._h, arr, len(row_ptrs), int(n_common), _p(series),
-                                                 stream), "tml_combined_series")
+        _abi.check(self._lib.tml_combined_series(self._h, arr, len(row_ptrs), int(n_common), int(first_col),
+                                                 int(n_cols), _p(series), stream), "tml_combined_series")
 
     def win_reduce(self, rows, mask: int, n_common: int, shard_lo: int,
                    shard_hi: int, series, stream: int = 0) -> None:

@@ -12,6 +12,9 @@ touches the training stream.
 Same class name, constructor meaning, ``compute_cli`` / ``compute_dashboard`` entry
 points, stale handling and result shape (``asdict(StepCombinedTimeResult)``) as the
 reference; only the data source differs (engines + a comm instead of a db path).
+
+``StepMemoryMetricsComputer`` is the same for the step-memory panel
+(``renderers/step_memory/{computer,cli_compute,common}.py``).
 """
 
 from __future__ import annotations
@@ -22,22 +25,99 @@ from typing import Any, Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import _abi
 from .reduce import LocalComm
+
+KIND_TIME, KIND_MEM = _abi.KIND_TIME, _abi.KIND_MEM
 
 # renderers/step_time/schema.py / compute.py:25-36 -- phase order of the 64-B row
 DEFAULT_METRIC_KEYS = ("dataloader_fetch", "h2d", "forward", "backward", "optimizer_step", "step_time")
 DEFAULT_HEATMAP_KEYS = ("dataloader_fetch", "h2d", "forward", "backward", "optimizer_step",
                         "wait_proxy", "step_time")
 _COL = {k: i for i, k in enumerate(DEFAULT_METRIC_KEYS)}
-_INFO_LEN = 5
-_ALIGN_LEN = 8
+_INFO_LEN = 7
+_ALIGN_LEN = 10
 
 
 def _empty(msg: str) -> Dict[str, Any]:
     return {"metrics": [], "status_message": msg, "rank_heatmap": None}
 
 
-class StepCombinedComputer:
+class _TickStages:
+    """The device stages both live views share (``csrc/tml_combined.cuh``): bounds
+    exchange, presence intersection, select + per-rank window values, row exchange and
+    the per-step series kernel.  ``self.engines / comm / L / device`` come from the user."""
+
+    def _sid(self) -> int:
+        if self.device.type != "cuda":
+            return 0
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _bounds(self, kind: int, lookback: int, sid: int) -> Dict[int, List[int]]:
+        """K7a per local rank + one small all-gather:
+        rank -> [n_rows, n_cand, lo, hi, latest, first_step, truncated]."""
+        flat: List[float] = []
+        for e in self.engines:
+            i = e.combined_prepare(kind, lookback, sid)
+            flat += [int(i.n_rows), int(i.n_cand), int(i.lo), int(i.hi), int(i.latest_step),
+                     int(i.first_step), int(i.truncated)]
+        infos: Dict[int, List[int]] = {}
+        for p, row in enumerate(self.comm.all_gather_vec(flat, self.device)):
+            for l in range(self.L):
+                infos[p * self.L + l] = [int(round(x)) for x in row[l * _INFO_LEN:(l + 1) * _INFO_LEN]]
+        return infos
+
+    def _intersect(self, kind: int, glo: int, span: int, window: int, sid: int):
+        """K7b presence -> MIN all-reduce -> K7c select.  Returns (n_common, presence,
+        local aligns, {rank: [sums x 6, peaks x 2]} for the ranks that own rows)."""
+        dev = self.device
+        presence = None
+        for e in self.engines:
+            p = torch.empty(span, dtype=torch.uint8, device=dev)
+            e.combined_presence(kind, glo, span, p, sid)
+            presence = p if presence is None else torch.minimum(presence, p)
+        self.comm.all_reduce_min_(presence)
+        flat: List[float] = []
+        aligns = []
+        for e in self.engines:
+            a = e.combined_select(kind, glo, span, presence, window, sid)
+            aligns.append(a)
+            flat += [int(a.n_common), int(a.n_rows)] + [float(x) for x in a.sums] + [float(x) for x in a.peaks]
+        vals: Dict[int, List[float]] = {}
+        for p, row in enumerate(self.comm.all_gather_vec(flat, dev)):
+            for l in range(self.L):
+                v = row[l * _ALIGN_LEN:(l + 1) * _ALIGN_LEN]
+                if int(round(v[1])) > 0:
+                    vals[p * self.L + l] = [float(x) for x in v[2:10]]
+        return int(aligns[0].n_common), presence, aligns, vals
+
+    def _series(self, kind, present, aligns, n, glo, presence, first_col, n_cols, sid):
+        """One row exchange (all-gather of n x 64 B per rank), then every rank reduces the
+        small window itself: [n_cols][median, worst, sum][n] + the step ids."""
+        dev = self.device
+        local = torch.zeros(self.L, n * 8, dtype=torch.float64, device=dev)
+        owner = None
+        for l, e in enumerate(self.engines):
+            if int(aligns[l].n_rows) > 0:
+                local[l].copy_(e.combined_rows_tensor(kind, n))
+                owner = e if owner is None else owner
+        if self.comm.world == 1:
+            allrows = local.view(1, self.L, n * 8)
+        else:
+            allrows = torch.empty(self.comm.world, self.L, n * 8, dtype=torch.float64, device=dev)
+            self.comm.all_gather_into(allrows.view(-1), local.view(-1))
+        ptrs = [allrows[r // self.L, r % self.L].data_ptr() for r in present]
+        out = torch.empty(n_cols * 3, n, dtype=torch.float64, device=dev)
+        self.engines[0].combined_series(ptrs, n, first_col, n_cols, out, sid)
+        series = out.cpu().numpy()
+        if owner is not None:
+            steps = owner.combined_steps(kind, n, sid)
+        else:  # this process holds no rows: the reduced presence bytes name the steps
+            steps = (torch.nonzero(presence).flatten()[-n:] + glo).cpu().tolist()
+        return series, [int(s) for s in steps]
+
+
+class StepCombinedComputer(_TickStages):
     """compute.py:38-128 (constructor, ``compute_cli``, ``compute_dashboard``, ``_compute``)."""
 
     def __init__(self, engines: Sequence[Any], comm: Any = None, *, window_size: int = 100,
@@ -99,25 +179,11 @@ class StepCombinedComputer:
         return _empty("No fresh step-combined data")
 
     # ------------------------------------------------------------------ core
-    def _sid(self) -> int:
-        if self.device.type != "cuda":
-            return 0
-        return int(torch.cuda.current_stream(self.device).cuda_stream)
-
     def _compute_impl(self, *, include_series: bool, include_rank_heatmap: bool) -> Dict[str, Any]:
         t0 = time.perf_counter()
-        dev, sid, W = self.device, self._sid(), self.window_size
+        sid, W = self._sid(), self.window_size
         lookback = max(W * self.lookback_factor, W)  # compute.py:366-368
-
-        # ---- K7a per local rank + bounds exchange
-        flat: List[float] = []
-        for e in self.engines:
-            i = e.combined_prepare(lookback, sid)
-            flat += [int(i.n_rows), int(i.n_cand), int(i.lo), int(i.hi), int(i.latest_step)]
-        infos: Dict[int, List[int]] = {}
-        for p, row in enumerate(self.comm.all_gather_vec(flat, dev)):
-            for l in range(self.L):
-                infos[p * self.L + l] = [int(round(x)) for x in row[l * _INFO_LEN:(l + 1) * _INFO_LEN]]
+        infos = self._bounds(KIND_TIME, lookback, sid)
         ranks = sorted(r for r, v in infos.items() if v[0] > 0)  # compute.py:139-143
         if not ranks:
             return _empty("No ranks available")
@@ -127,67 +193,21 @@ class StepCombinedComputer:
         if ghi < glo:
             return _empty("No common step window yet")
         span = ghi - glo + 1
-
-        # ---- K7b presence -> intersection -> K7c select + window sums
-        presence = None
-        for e in self.engines:
-            p = torch.empty(span, dtype=torch.uint8, device=dev)
-            e.combined_presence(glo, span, p, sid)
-            presence = p if presence is None else torch.minimum(presence, p)
-        self.comm.all_reduce_min_(presence)
-        flat = []
-        aligns = []
-        for e in self.engines:
-            a = e.combined_select(glo, span, presence, W, sid)
-            aligns.append(a)
-            flat += [int(a.n_common), int(a.n_rows)] + [float(x) for x in a.sums]
-        n = int(aligns[0].n_common)
+        n, presence, aligns, vals = self._intersect(KIND_TIME, glo, span, W, sid)
         if n == 0:
             return _empty("No common step window yet")
-        sums: Dict[int, List[float]] = {}
-        for p, row in enumerate(self.comm.all_gather_vec(flat, dev)):
-            for l in range(self.L):
-                v = row[l * _ALIGN_LEN:(l + 1) * _ALIGN_LEN]
-                r = p * self.L + l
-                if r in ranks and int(round(v[1])) > 0:
-                    sums[r] = [float(x) for x in v[2:8]]
+        sums = {r: v[:6] for r, v in vals.items() if r in ranks}
         present = [r for r in ranks if r in sums]
         coverage = {"expected_steps": W, "steps_used": n, "completed_step": int(completed),
                     "world_size": len(ranks), "ranks_present": len(present),
                     "incomplete": len(present) < len(ranks)}
-
-        # ---- K7d series (CLI mode): one row exchange, every rank reduces the tiny window
         steps: List[int] = []
         series = None
-        if include_series:
-            series, steps = self._series(present, aligns, n, glo, presence, sid)
-
+        if include_series:  # CLI mode
+            series, steps = self._series(KIND_TIME, present, aligns, n, glo, presence, 0, 6, sid)
         result = self._assemble(present, sums, coverage, steps, series, include_rank_heatmap)
         self.last_timings_ms = {"tick": (time.perf_counter() - t0) * 1e3}
         return result
-
-    def _series(self, present, aligns, n, glo, presence, sid):
-        dev = self.device
-        local = torch.zeros(self.L, n * 8, dtype=torch.float64, device=dev)
-        owner = None
-        for l, e in enumerate(self.engines):
-            if int(aligns[l].n_rows) > 0:
-                local[l].copy_(e.combined_rows_tensor(n))
-                owner = e if owner is None else owner
-        if self.comm.world == 1:
-            allrows = local.view(1, self.L, n * 8)
-        else:
-            allrows = torch.empty(self.comm.world, self.L, n * 8, dtype=torch.float64, device=dev)
-            self.comm.all_gather_into(allrows.view(-1), local.view(-1))
-        ptrs = [allrows[r // self.L, r % self.L].data_ptr() for r in present]
-        out = torch.empty(18, n, dtype=torch.float64, device=dev)
-        self.engines[0].combined_series(ptrs, n, out, sid)
-        series = out.cpu().numpy()
-        if owner is not None:
-            steps = owner.combined_steps(n, sid)
-        else:  # this process holds no rows: the reduced presence bytes name the steps
-            steps = (torch.nonzero(presence).flatten()[-n:] + glo).cpu().tolist()
-        return series, [int(s) for s in steps]
 
     # ------------------------------------------------------------------ rank-level (O(R) scalars)
     def _assemble(self, present, sums, coverage, steps, series, include_rank_heatmap):
@@ -260,3 +280,140 @@ class StepCombinedComputer:
                             "worst_rank": worst_rank, "skew_ratio": float(skew_ratio),
                             "skew_pct": float(skew_pct)},
                 "coverage": coverage}
+
+
+# =============================================================================== step memory
+_MEM_COL = {"peak_allocated": 0, "peak_reserved": 1}
+_NO_GPU = "No GPU detected. Step memory uses torch-based GPU memory telemetry."
+
+
+class StepMemoryCombinedComputer(_TickStages):
+    """One window size of the step-memory panel: ``build_step_memory_combined_result``
+    (common.py:215-356) + the stale wrapper of ``StepMemoryCLIComputer.compute``
+    (cli_compute.py:44-88)."""
+
+    def __init__(self, engines: Sequence[Any], comm: Any = None, *, window_size: int = 100,
+                 stale_ttl_s: Optional[float] = 30.0, metric_keys: Sequence[str] = ("peak_allocated",
+                                                                                     "peak_reserved"),
+                 gpu_available: Optional[bool] = None, device: Optional[torch.device] = None,
+                 use_side_stream: bool = True) -> None:
+        self.engines = list(engines)
+        self.comm = comm or LocalComm()
+        self.L = len(self.engines)
+        self.window_size = int(window_size)
+        self.metric_keys = [k for k in metric_keys]
+        self.device = device or torch.device("cuda", self.engines[0].device)
+        # the reference reads MAX(gpu_available) from process/system samples (common.py:78-112)
+        self.gpu_available = (torch.cuda.is_available() if gpu_available is None and self.device.type == "cuda"
+                              else gpu_available)
+        self._stream = None
+        if use_side_stream and self.device.type == "cuda":
+            self._stream = torch.cuda.Stream(device=self.device)
+        self._last_ok: Optional[Dict[str, Any]] = None
+        self._last_ok_ts = 0.0
+        self._stale_ttl_s = float(stale_ttl_s) if stale_ttl_s is not None else None
+
+    def compute(self) -> Dict[str, Any]:
+        try:
+            if self._stream is not None:
+                with torch.cuda.stream(self._stream):
+                    out = self._compute_impl()
+            else:
+                out = self._compute_impl()
+        except Exception:  # noqa: BLE001
+            return self._stale_or_empty("STALE (exception)")
+        if not out["metrics"]:
+            if "No GPU detected" in str(out["status_message"]):  # cli_compute.py:60-64
+                self._last_ok, self._last_ok_ts = None, 0.0
+                return out
+            return self._stale_or_empty("STALE (no metrics this tick)")
+        self._last_ok, self._last_ok_ts = out, time.time()
+        return out
+
+    def _stale_or_empty(self, msg: str) -> Dict[str, Any]:
+        if self._last_ok is not None and (self._stale_ttl_s is None
+                                          or (time.time() - self._last_ok_ts) <= self._stale_ttl_s):
+            return {"metrics": self._last_ok["metrics"], "status_message": msg}
+        return {"metrics": [], "status_message": "No complete memory metrics available"}
+
+    def _compute_impl(self) -> Dict[str, Any]:
+        sid = self._sid()
+        ws = max(1, int(self.window_size))
+        scan_span = max(ws * 20, ws + 1)                     # common.py:245
+        lookback = scan_span + 64                            # room for re-flushed step ids
+        infos = self._bounds(KIND_MEM, lookback, sid)
+        ranks = sorted(r for r, v in infos.items() if v[0] > 0)
+        if not ranks:                                        # common.py:235-239
+            return {"metrics": [], "status_message": "Waiting for first fully completed step across all ranks…"}
+        world_size = len(ranks)
+        completed = min(infos[r][4] for r in ranks)
+        start = max(0, completed - scan_span + 1)
+        # a rank far ahead (or full of re-flushed ids) may need older rows than the first
+        # look-back held: widen locally -- its bounds in `infos` do not change
+        for l, e in enumerate(self.engines):
+            v = infos[self.comm.index * self.L + l]
+            lb, first, trunc = lookback, v[5], v[6]
+            while trunc and first > start:
+                lb *= 4
+                i = e.combined_prepare(KIND_MEM, lb, sid)
+                first, trunc = int(i.first_step), int(i.truncated)
+                if int(i.n_rows) < lb:  # clamped by the ring: nothing older is retained
+                    break
+        span = completed - start + 1
+        n, presence, aligns, vals = self._intersect(KIND_MEM, start, span, ws, sid)
+        present = sorted(r for r in vals if r in ranks)
+        out: List[Dict[str, Any]] = []
+        if n > 0 and present:
+            series, steps = self._series(KIND_MEM, present, aligns, n, start, presence, 6, 2, sid)
+            for key in self.metric_keys:
+                c = _MEM_COL.get(key)
+                if c is None:
+                    continue
+                peaks = np.array([vals[r][6 + c] for r in present], dtype=np.float64)  # common.py:289-300
+                median_peak = float(np.median(peaks))
+                worst_peak = float(np.max(peaks))
+                worst_rank = int(present[int(np.argmax(peaks))])
+                skew_ratio = (worst_peak / median_peak) if median_peak > 0.0 else 0.0
+                skew_pct = ((worst_peak - median_peak) / median_peak) if median_peak > 0.0 else 0.0
+                out.append({
+                    "metric": str(key), "device": self._device_label(),
+                    "series": {"steps": list(steps), "median": series[c * 3].tolist(),
+                               "worst": series[c * 3 + 1].tolist()},
+                    "summary": {"window_size": ws, "steps_used": n, "median_peak": median_peak,
+                                "worst_peak": worst_peak, "worst_rank": worst_rank,
+                                "skew_ratio": float(skew_ratio), "skew_pct": float(skew_pct)},
+                    "coverage": {"expected_steps": ws, "steps_used": n, "completed_step": int(completed),
+                                 "world_size": int(world_size), "ranks_present": len(present),
+                                 "incomplete": len(present) < world_size},
+                })
+        if out:
+            status = "OK"
+        elif self.gpu_available is False:  # the rank that fixes `completed` has a row in the window
+            status = _NO_GPU
+        else:
+            status = "No complete memory metrics available"
+        return {"metrics": out, "status_message": status}
+
+    def _device_label(self) -> Optional[str]:
+        """The reference reports the majority device string over ranks, ties broken by
+        Python set order (common.py:400-408); one label here only when it is unambiguous."""
+        if self.comm.world * self.L == 1 and self.device.type == "cuda":
+            return f"cuda:{self.device.index or 0}"
+        return None
+
+
+class StepMemoryMetricsComputer:
+    """computer.py:20-50: the facade the renderers hold."""
+
+    def __init__(self, engines: Sequence[Any], comm: Any = None, *, stale_ttl_s: Optional[float] = 30.0,
+                 cli_window_size: int = 400, dashboard_window_size: int = 400, **kw: Any) -> None:
+        self._cli = StepMemoryCombinedComputer(engines, comm, window_size=cli_window_size,
+                                               stale_ttl_s=stale_ttl_s, **kw)
+        self._dashboard = StepMemoryCombinedComputer(engines, comm, window_size=dashboard_window_size,
+                                                     stale_ttl_s=stale_ttl_s, **kw)
+
+    def compute_cli(self) -> Dict[str, Any]:
+        return self._cli.compute()
+
+    def compute_dashboard(self) -> Dict[str, Any]:
+        return self._dashboard.compute()

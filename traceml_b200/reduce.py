@@ -75,6 +75,7 @@ class TorchDistComm:
 
         self._dist = dist
         self.group = group
+        self.n_vec = 0  # small vector all-gathers issued (the latency-bound exchanges)
         self.world = dist.get_world_size(group)
         self.index = dist.get_rank(group)
 
@@ -85,6 +86,7 @@ class TorchDistComm:
 
     def all_gather_vec(self, vec, device=None) -> List[List[float]]:
         """Fixed-length f64 vectors: one small all-gather, no pickling."""
+        self.n_vec += 1
         dev = device or torch.device("cpu")
         inp = torch.tensor(list(vec), dtype=torch.float64, device=dev)
         out = torch.empty(self.world * inp.numel(), dtype=torch.float64, device=dev)
@@ -192,7 +194,8 @@ class WindowReducer:
     """Sequences the reduce stages for the local engines of this process."""
 
     def __init__(self, engines: Sequence[Any], comm: Any = None, *, device: Optional[torch.device] = None,
-                 exchange: str = "auto"):
+                 exchange: str = "auto", speculate: bool = True):
+        self.speculate = speculate
         self.engines = list(engines)
         self.comm = comm or LocalComm()
         self.device = device or torch.device("cuda", self.engines[0].device)
@@ -263,26 +266,43 @@ class WindowReducer:
         if ev:
             k3a_ev = torch.cuda.Event(enable_timing=True)
             k3a_ev.record()
-        per = _INFO_LEN + (_PROC_LEN if proc_rows else 0)
+        # Lock-step speculation: a rank whose own time window is dense assumes the common
+        # window IS its window (true whenever the ranks run in lock step) and sends that
+        # alignment -- sums and rows handle, nothing to launch -- with its bounds.  If the
+        # gathered bounds confirm it, the separate alignment exchange is skipped.
+        plen = _PROC_LEN if proc_rows else 0
+        slen = self._spec_len()
+        per = _INFO_LEN + plen + slen
         flat: List[float] = []
         for l, d in enumerate(local_infos):
             flat.extend(self._info_pack(d))
+            eng = self.engines[l]
             if proc_rows:  # process aggregates (K6) ride in the same exchange
-                eng = self.engines[l]
                 a = (eng.proc_reduce_collect() if hasattr(eng, "proc_reduce_collect")
                      else eng.proc_reduce(max(1, int(proc_rows)), stream))
                 flat.extend(float(getattr(a, f)) for f in _PROC_FIELDS)
+            if slen:
+                sp = [0.0] * slen
+                if d["dense"][KIND_TIME] and d["n_cand"][KIND_TIME] > 0:
+                    a = eng.win_select_dense(KIND_TIME, d["lo"][KIND_TIME], d["n_cand"][KIND_TIME], stream)
+                    sp = self._align_pack(eng, KIND_TIME, a, slen)
+                flat.extend(sp)
         infos: Dict[int, Dict[str, Any]] = {}
         proc_aggs: Dict[int, Dict[str, Any]] = {}
+        spec: Optional[List[List[float]]] = [] if slen else None
         for p, row in enumerate(self.comm.all_gather_vec(flat, dev)):
+            srow: List[float] = []
             for l in range(self.L):
                 v = row[l * per:(l + 1) * per]
                 infos[p * self.L + l] = self._info_unpack(v[:_INFO_LEN])
                 if proc_rows:
-                    pa = dict(zip(_PROC_FIELDS, v[_INFO_LEN:]))
+                    pa = dict(zip(_PROC_FIELDS, v[_INFO_LEN:_INFO_LEN + plen]))
                     for f in _PROC_INT_FIELDS:
                         pa[f] = int(round(pa[f]))
                     proc_aggs[p * self.L + l] = pa
+                srow.extend(v[_INFO_LEN + plen:])
+            if spec is not None:
+                spec.append(srow)
         ranks = sorted(infos)
         hw.append(_time.perf_counter())
         if ev:
@@ -292,7 +312,7 @@ class WindowReducer:
         # common case: ring not longer than the window, every step has memory), one
         # alignment serves both sections.
         merged = all(d["n_cand"][0] == d["n_cand"][1] == d["n_both"] for d in infos.values())
-        t_res = self._align(KIND_TIME, window, infos, ranks, stream)
+        t_res = self._align(KIND_TIME, window, infos, ranks, stream, spec=spec)
         if merged:
             m_res = KindResult(observed=t_res.observed, used=list(t_res.used), n_common=t_res.n_common,
                                start_step=t_res.start_step, end_step=t_res.end_step,
@@ -348,7 +368,14 @@ class WindowReducer:
                             exchange=mode, fused_pass=same, timings_ms=timings, proc_aggs=proc_aggs)
 
     # ------------------------------------------------------------------ alignment
-    def _align(self, kind: int, window: int, infos, ranks, stream) -> KindResult:
+    def _spec_len(self) -> int:
+        """Length of the speculative alignment block in the first exchange (0 = off)."""
+        if not self.speculate:
+            return 0
+        handles = self.comm.world > 1 and self.device.type == "cuda" and self.exchange in ("auto", "p2p")
+        return _ALIGN_LEN if handles else 15
+
+    def _align(self, kind: int, window: int, infos, ranks, stream, spec=None) -> KindResult:
         res = KindResult()
         part = [r for r in ranks if infos[r]["n_cand"][kind] > 0]
         res.observed = len(part)
@@ -361,6 +388,10 @@ class WindowReducer:
         span = ghi - glo + 1
         dev = self.device
         if all(infos[r]["dense"][kind] for r in part):
+            if (spec is not None and span <= window
+                    and all(infos[r]["lo"][kind] == glo and infos[r]["hi"][kind] == ghi for r in part)):
+                # every participant speculated on exactly [glo, ghi]: its block is the alignment
+                return self._parse_aligns(res, spec, self._spec_len(), part, infos)
             # lock-step fast path: every participant holds every step id of [glo, ghi]
             n_common = min(span, window)
             first = ghi - n_common + 1
@@ -381,23 +412,30 @@ class WindowReducer:
             flat.extend(self._align_pack(e, kind, a))
         return self._collect_aligns(kind, res, flat, part, infos)
 
-    def _align_pack(self, engine, kind, a) -> List[float]:
+    def _align_pack(self, engine, kind, a, length: Optional[int] = None) -> List[float]:
         """15 numbers + (p2p only) the rows' CUDA-IPC handle, so the peer mapping
-        needs no collective of its own."""
+        needs no collective of its own.  ``length`` fixes the block size (speculative
+        block: every rank must send the same layout before n_common is agreed)."""
         out = ([int(a.n_common), int(a.start_step), int(a.end_step), int(a.n_rows)]
                + [float(x) for x in a.t_sums] + [float(x) for x in a.m_sums])
-        if self._exchange_mode(int(a.n_common)) == "p2p":
+        p2p = self._exchange_mode(int(a.n_common)) == "p2p"
+        if p2p and (length is None or length == _ALIGN_LEN):
             handle = engine.win_rows_export(kind) if int(a.n_rows) > 0 else bytes(72)
             out += [float(b) for b in handle]
+        if length is not None:
+            out += [0.0] * (length - len(out))
         return out
 
     def _collect_aligns(self, kind, res, flat, part, infos) -> KindResult:
+        # n_common is identical on every rank, so every rank packed the same layout
+        alen = _ALIGN_LEN if len(flat) == _ALIGN_LEN * self.L else 15
+        return self._parse_aligns(res, self.comm.all_gather_vec(flat, self.device), alen, part, infos)
+
+    def _parse_aligns(self, res, rows, alen, part, infos) -> KindResult:
         res.handles = {}
         gathered = []
-        # n_common is identical on every rank, so every rank packed the same layout
-        p2p = len(flat) == _ALIGN_LEN * self.L
-        alen = _ALIGN_LEN if p2p else 15
-        for row in self.comm.all_gather_vec(flat, self.device):
+        p2p = alen == _ALIGN_LEN
+        for row in rows:
             lst = []
             for l in range(self.L):
                 v = row[l * alen:(l + 1) * alen]
