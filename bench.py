@@ -409,6 +409,14 @@ def main():
     e1.record()
     torch.cuda.synchronize(device); barrier(world)
     launches = eng.launch_count - l0
+    # stage breakdown (a diagnostic, outside the timed region: it adds a dozen torch events
+    # per step).  The two kernels' own times (k3a, k4) above come from the timed steps.
+    for _ in range(max(3, args.steps // 2)):
+        r2 = summ.build(W, 60_000, timings=True)
+        for k, v in r2["reduce"].timings_ms.items():
+            if k not in ("k3a", "k4"):
+                stage.setdefault(k, []).append(v)
+    torch.cuda.synchronize(device); barrier(world)
     clk = None
     if rank == 0:
         t_wait = time.time()

@@ -294,6 +294,9 @@ typedef struct tml_reduce_args {
  * columns: diagnostics/step_time/adapters.py:92-139,
  * reporting/sections/step_memory/model.py:141-176. */
 int tml_win_reduce(tml_ctx* ctx, const tml_reduce_args* args, void* stream);
+/* Device time (ms, CUDA events on the launching stream) of the last k_window_rows
+ * (which = 0) / k_window_reduce (which = 1) launch; -1 if none or not finished. */
+double tml_kernel_ms(tml_ctx* ctx, uint32_t which);
 
 typedef struct tml_band_args {
   uint64_t n_common;

@@ -24,7 +24,7 @@ for r in range(R):
 torch.cuda.synchronize()
 summ = sections.SummaryEngine(engines, ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=R)
 for _ in range(reps):
-    out = summ.build(W, 60000)
+    out = summ.build(W, 60000, timings=True)
 torch.cuda.synchronize()
 print("ok", out["step_time"]["diagnosis"]["primary"]["status"], out["reduce"].timings_ms)
 

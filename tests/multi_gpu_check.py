@@ -43,7 +43,7 @@ def main():
             eng.load_procs(procs)
             torch.cuda.synchronize()
             res = sections.SummaryEngine([eng], TorchDistComm(), exchange=mode,
-                                         ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world).build(W, W)
+                                         ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world).build(W, W, timings=True)
             assert res["reduce"].exchange == mode
             results[mode] = res
             dist.barrier()

@@ -155,6 +155,7 @@ SIGNATURES = {
     "tml_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "tml_peer_close": (C.c_int, [vp, vp]),
     "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),
+    "tml_kernel_ms": (C.c_double, [vp, u32]),
     "tml_combined_prepare": (C.c_int, [vp, u32, u32, vp, C.POINTER(CombinedInfo)]),
     "tml_combined_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
     "tml_combined_select": (C.c_int, [vp, u32, u64, u64, vp, u32, vp, C.POINTER(CombinedAlign)]),

@@ -28,6 +28,8 @@
 #include <utility>
 #include <vector>
 
+#include <charconv>
+
 #include "../../include/traceml_b200.h"
 
 namespace {
@@ -57,7 +59,9 @@ S jstr(const S& s) {
 }
 S jnum(double v) {
   if (!isfinite(v)) return "null";
-  S s = fmt("%.17g", v);
+  char buf[40];  // shortest text that round-trips the double exactly (what Python's repr prints)
+  auto r = std::to_chars(buf, buf + sizeof(buf), v);
+  S s(buf, r.ptr);
   if (s.find_first_of(".eEn") == S::npos) s += ".0";  // keep it a JSON float
   return s;
 }

@@ -1187,6 +1187,7 @@ struct tml_ctx {
   tml_proc_record* h_pmirror = nullptr; tml_proc_record* d_pmirror = nullptr;
   // host-side step state (training thread)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of k_window_rows alone
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // device time of k_window_reduce alone
   u64 commits = 0;
   u64 launches = 0;  // kernels this context has launched (bench: gpu_launches)
   u32 next_slot = 0;
@@ -1871,6 +1872,8 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
   u64 need = ((a->shard_hi - a->shard_lo) * 4 + RD_THREADS - 1) / RD_THREADS;
   const u64 cap = (u64)c->n_sms * 8ull;
   const int grid = (int)(need < cap ? (need ? need : 1) : cap);
+  if (!c->ev2) { CK(cudaEventCreate(&c->ev2)); CK(cudaEventCreate(&c->ev3)); }
+  CK(cudaEventRecord(c->ev2, s));
   switch (a->n_ranks) {
     case 1: launch_reduce<1>(grid, s, p); break;
     case 2: launch_reduce<2>(grid, s, p); break;
@@ -1883,8 +1886,18 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
     default: k_window_reduce_any<<<grid, RD_THREADS, 0, s>>>(p); break;
   }
   CK(cudaPeekAtLastError());
+  CK(cudaEventRecord(c->ev3, s));
   c->launches += 1;
   return TML_OK;
+}
+
+double tml_kernel_ms(tml_ctx* c, uint32_t which) {
+  if (!c || which > 1) return -1.0;
+  cudaEvent_t a = which == 0 ? c->ev0 : c->ev2, b = which == 0 ? c->ev1 : c->ev3;
+  if (!a || !b) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+  return (double)ms;
 }
 
 int tml_win_bands(tml_ctx* c, const double* series, const tml_band_args* a, void* stream,

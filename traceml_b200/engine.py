@@ -204,6 +204,10 @@ class Engine:
         _abi.check(self._lib.tml_peer_open(self._h, handle[:64], C.byref(p)), "tml_peer_open")
         return int(p.value) + int.from_bytes(handle[64:72], "little")
 
+    def kernel_ms(self, which: int) -> float:
+        """Device time of the last K3a (0) / K4 (1) launch, from the library's own events."""
+        return float(self._lib.tml_kernel_ms(self._h, int(which)))
+
     # ---- live tick (StepCombined / step-memory combined twins): header "LIVE TICK"
     def combined_prepare(self, kind: int, lookback: int, stream: int = 0) -> _abi.CombinedInfo:
         out = _abi.CombinedInfo()

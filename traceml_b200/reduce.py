@@ -236,20 +236,24 @@ class WindowReducer:
                 "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20]), "dense": [i(v[21]), i(v[22])]}
 
     def reduce(self, window: int, *, want_series: bool = False,
-               proc_rows: Optional[int] = None, overlap=None) -> ReduceOutput:
+               proc_rows: Optional[int] = None, overlap=None, stage_timings: bool = False) -> ReduceOutput:
         """``overlap(proc_aggs)``: host work that needs only the process aggregates; it
-        runs after K4 has been launched and before the first wait on it."""
+        runs after K4 has been launched and before the first wait on it.
+        ``stage_timings``: per-stage CUDA-event / host-clock breakdown (a diagnostic: a dozen torch
+        events per call).  Without it ``timings_ms`` still carries ``k3a`` / ``k4``, the
+        two kernels' device times from the library's own events."""
         window = max(1, int(window))
         dev = self.device
         stream = _stream_of(dev)
         self._k4_events = []
+        self._timed = bool(stage_timings)
         R = self.comm.world * self.L
         ev = None
         timings: Dict[str, float] = {}
         import time as _time
 
         hw = [_time.perf_counter()]
-        if dev.type == "cuda":
+        if stage_timings and dev.type == "cuda":
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             ev[0].record()
 
@@ -362,8 +366,11 @@ class WindowReducer:
             timings["k3a"] = max((d.get("kernel_ms", 0.0) for d in local_infos), default=0.0) \
                 or timings["k3a_stage"]
             timings["k4"] = float(sum(a.elapsed_time(b) for a, b in self._k4_events))
-        if not want_series:
-            pass
+        elif dev.type == "cuda":  # the bands stage synchronised: both kernels have finished
+            timings["k3a"] = max((d.get("kernel_ms", 0.0) for d in local_infos), default=0.0)
+            if t_res.n_common or m_res.n_common:
+                timings["k4"] = float(sum(max(0.0, e.kernel_ms(1)) for e in self.engines
+                                          if hasattr(e, "kernel_ms")))
         return ReduceOutput(window=window, ranks=ranks, infos=infos, time=t_res, mem=m_res,
                             exchange=mode, fused_pass=same, timings_ms=timings, proc_aggs=proc_aggs)
 
@@ -538,7 +545,7 @@ class WindowReducer:
         # step-sharded: shard s of W_total shards -> engine with global rank s
         W = self.comm.world * self.L
         lo_first, hi_last = None, None
-        timed = self.device.type == "cuda"
+        timed = self._timed and self.device.type == "cuda"
         if timed:
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             k0.record()

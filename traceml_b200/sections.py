@@ -281,7 +281,7 @@ class SummaryEngine:
         self.ram_total = ram_total
         self.gpu_count = gpu_count
 
-    def build(self, window: int = 10_000, proc_rows: int = 10_000) -> Dict[str, Any]:
+    def build(self, window: int = 10_000, proc_rows: int = 10_000, *, timings: bool = False) -> Dict[str, Any]:
         import torch
 
         gpu_count = self.gpu_count if self.gpu_count is not None else torch.cuda.device_count()
@@ -300,7 +300,8 @@ class SummaryEngine:
             box["process"] = build_process(aggs)
 
         # the process rules need only the first exchange: they run under the K4 launch
-        out = self.reducer.reduce(window, proc_rows=max(1, int(proc_rows)), overlap=_process)
+        out = self.reducer.reduce(window, proc_rows=max(1, int(proc_rows)), overlap=_process,
+                                  stage_timings=timings)
         aggs = box["aggs"]
         with_gpu = [a for a in aggs.values() if a["n_gpu"] > 0]
         gpu_total = max((a["max_total"] for a in with_gpu), default=None)
