@@ -289,6 +289,54 @@ def step_overhead(device, world, local, quick=False):
     xs = [torch.randn(64, 3, 224, 224).pin_memory() for _ in range(2)]
     ys = [torch.randint(0, 10, (64,)).pin_memory() for _ in range(2)]
     harness("resnet18_b64", model, xs, ys, 8 if quick else 24, 2 if quick else 3)
+
+    # live render tick (StepCombined / step-memory twins) across the job's ranks, next to the
+    # reference's computation (oracle port, rows pre-parsed: no SQLite / JSON) on rank 0
+    try:
+        import torch.distributed as dist
+        from oracle import live_oracle
+        from traceml_b200 import records as rec_mod
+        from traceml_b200 import replay
+        from traceml_b200.engine import Engine
+        from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
+        from traceml_b200.reduce import LocalComm, TorchDistComm
+
+        rank = dist.get_rank() if world > 1 else 0
+        S = 2000
+        mine = replay.make_step_replay("input_straggler", world, S, seed=3, only_ranks=[rank])[rank]
+        le = Engine(device=local, rank=rank, world=world, ring_slots=4096, proc_slots=64)
+        le.load_steps(mine)
+        torch.cuda.synchronize(device)
+        comm = TorchDistComm() if world > 1 else LocalComm()
+        tick_t = StepCombinedComputer([le], comm, window_size=100)
+        tick_m = StepMemoryCombinedComputer([le], comm, window_size=400)
+
+        def tick_ms(fn, n=30):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter(); fn(); ts.append((time.perf_counter() - t0) * 1e3)
+            return statistics.median(ts)
+
+        live = {"step_time_cli_ms": tick_ms(tick_t.compute_cli),
+                "step_time_dashboard_ms": tick_ms(tick_t.compute_dashboard),
+                "step_memory_ms": tick_ms(tick_m.compute), "ranks": world,
+                "window": {"step_time": 100, "step_memory": 400}}
+        le.close()
+        if rank == 0:
+            allr = replay.make_step_replay("input_straggler", world, S, seed=3)
+            rows = {r: [rec_mod.step_record_to_wire(x, device=f"cuda:{r}") for x in allr[r][-400:]]
+                    for r in allr}
+            mrows = {r: [(int(s_), float(a_), float(v_)) for s_, a_, v_ in
+                         zip(allr[r]["step"], allr[r]["peak_alloc"], allr[r]["peak_resv"])] for r in allr}
+            live["reference_port_step_time_cli_ms"] = tick_ms(
+                lambda: live_oracle.live_step_time(rows, window=100), n=5)
+            live["reference_port_step_memory_ms"] = tick_ms(
+                lambda: live_oracle.live_step_memory(mrows, window=400), n=5)
+        out["live_tick"] = live
+    except Exception as exc:
+        out["live_tick"] = {"error": f"{type(exc).__name__}: {exc}"}
     return out
 
 
