@@ -344,6 +344,72 @@ int tml_proc_reduce(tml_ctx* ctx, uint32_t max_rows, void* stream,
 int tml_proc_reduce_launch(tml_ctx* ctx, uint32_t max_rows, void* stream);
 int tml_proc_reduce_collect(tml_ctx* ctx, tml_proc_agg* out);
 
+/* ---------------------------------------------------------------- WHOLE REDUCE
+ * The staged reduce above, sequenced natively for the production layout (one rank
+ * per process / GPU): prepare -> bounds exchange (+ process aggregates + the
+ * lock-step speculative alignment) -> alignment -> row exchange fused into K4
+ * (peer loads) or step-sharded NCCL send/recv -> K4 -> trend bands -> band
+ * exchange.  Replaces, for one call of final_summary(), the load + align + reduce
+ * half of StepTimeSummarySection / StepMemorySummarySection / ProcessSummarySection
+ * (reporting/sections/{step_time,step_memory,process}/__init__.py:50-112); the
+ * rank-level rules are then one tml_diag_* call each.
+ * The collectives are NCCL calls on the communicator the host side hands in (the
+ * training job's own: torch.distributed's ncclComm_t), issued on `stream`.       */
+typedef struct tml_comm {
+  void* nccl_comm;   /* ncclComm_t spanning the job's ranks; NULL when world == 1 */
+  int32_t rank;
+  int32_t world;
+} tml_comm;
+
+#define TML_XCHG_AUTO 0u  /* peer loads for large / repeated windows, else send-recv */
+#define TML_XCHG_P2P 1u   /* CUDA-IPC peer loads fused into K4                      */
+#define TML_XCHG_A2A 2u   /* step-sharded ncclSend/ncclRecv, K4 on the received shard */
+#define TML_XCHG_LOCAL 3u /* world == 1 (reported, not requested)                    */
+
+typedef struct tml_reduce_run_args {
+  uint32_t window;      /* max_rows / window_size of the sections                 */
+  uint32_t proc_rows;   /* max process rows (0: skip the process aggregates)      */
+  uint32_t exchange;    /* TML_XCHG_*                                             */
+  uint32_t speculate;   /* 1: lock-step speculation (alignment rides exchange #1) */
+} tml_reduce_run_args;
+
+typedef struct tml_kind_result {
+  uint32_t observed;                 /* ranks that had candidates                 */
+  uint32_t n_used;                   /* ranks with rows in the aligned window     */
+  int32_t used[TML_MAX_RANKS];       /* ascending                                 */
+  uint64_t n_common, start_step, end_step;
+  uint64_t n_rows[TML_MAX_RANKS];    /* by position in used[]                     */
+  double t_sums[TML_MAX_RANKS][7];
+  double m_sums[TML_MAX_RANKS][4];
+  uint32_t has_bands;
+  uint32_t _pad;
+  double band_sum[TML_SERIES_PER_STEP][3];   /* summed over ranks, rank order     */
+  uint64_t band_cnt[TML_SERIES_PER_STEP][3];
+  double tail_first[TML_SERIES_PER_STEP];
+  double tail_last[TML_SERIES_PER_STEP];
+  uint64_t shard_lo, shard_hi;       /* this rank's columns of the series         */
+  const double* series;              /* device, [16][n_common]; owned by the ctx  */
+} tml_kind_result;
+
+typedef struct tml_reduce_run_out {
+  uint32_t n_ranks;
+  uint32_t exchange_used;            /* TML_XCHG_*                                */
+  uint32_t fused_pass;               /* time and memory shared one K4 pass        */
+  uint32_t n_exchanges;              /* small vector exchanges issued             */
+  tml_win_info infos[TML_MAX_RANKS];
+  tml_proc_agg procs[TML_MAX_RANKS];
+  tml_kind_result time, mem;
+  double k3a_ms, k4_ms;              /* device time of the two bandwidth kernels  */
+  double stage_ms[5];                /* host clock: prepare, align, reduce (launch), bands, total */
+} tml_reduce_run_out;
+
+int tml_reduce_run(tml_ctx* ctx, const tml_comm* comm, const tml_reduce_run_args* args,
+                   void* stream, tml_reduce_run_out* out);
+
+/* sizeof() of an ABI struct by name ("tml_win_info", ...), 0 if unknown: lets a binding
+ * verify its mirror of the layouts without compiling C. */
+uint64_t tml_struct_size(const char* name);
+
 /* ---------------------------------------------------------------- LIVE TICK
  * The render-tick twins of the window reduce: what the reference's live CLI /
  * dashboard recompute every second from SQLite.

@@ -36,16 +36,26 @@ def main():
                 replay.make_step_replay(scenario, world, S, seed=11, only_ranks=[rank])[rank])
         procs = replay.make_proc_replay("overhang", world, 500, seed=11, only_ranks=[rank])[rank]
         results = {}
-        for mode in ("p2p", "nccl", "a2a"):
+        # (label, exchange, native sequencing): the C++ driver (tml_reduce_run, NCCL on torch's
+        # communicator) and the Python driver must agree bit for bit
+        for label, mode, native in (("p2p", "p2p", True), ("nccl", "nccl", False), ("a2a", "a2a", True),
+                                    ("p2p_py", "p2p", False), ("a2a_py", "a2a", False), ("auto", "auto", True)):
             eng = Engine(device=local, rank=rank, world=world, ring_slots=max(64, len(mine) + 8), proc_slots=1024)
             if len(mine):
                 eng.load_steps(mine)
             eng.load_procs(procs)
             torch.cuda.synchronize()
-            res = sections.SummaryEngine([eng], TorchDistComm(), exchange=mode,
-                                         ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world).build(W, W, timings=True)
-            assert res["reduce"].exchange == mode
-            results[mode] = res
+            se = sections.SummaryEngine([eng], TorchDistComm(), exchange=mode, native=native,
+                                        ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world)
+            assert se.reducer._native_ok() == native, (label, se.reducer._native_ok())
+            res = se.build(W, W)
+            import time as _t
+            torch.cuda.synchronize(); dist.barrier(); t0 = _t.perf_counter()
+            res = se.build(W, W)
+            torch.cuda.synchronize(); res["_ms"] = (_t.perf_counter() - t0) * 1e3
+            if mode != "auto":
+                assert res["reduce"].exchange == mode, (label, res["reduce"].exchange)
+            results[label] = res
             dist.barrier()
             eng.close()
         if rank == 0:
@@ -53,8 +63,11 @@ def main():
                 a, b = results["p2p"], results["nccl"]
                 assert_struct(plain(a["step_time"]), plain(b["step_time"]), f"{scenario}: p2p == nccl", rel=0.0)
                 c = results["a2a"]
-                assert_struct(plain(a["step_time"]), plain(c["step_time"]), f"{scenario}: p2p == a2a", rel=0.0)
-                assert_struct(plain(a["step_memory"]["diagnosis"]), plain(c["step_memory"]["diagnosis"]), "mem p2p == a2a", rel=0.0)
+                for other in ("a2a", "p2p_py", "a2a_py", "auto"):
+                    o_ = results[other]
+                    assert_struct(plain(a["step_time"]), plain(o_["step_time"]), f"{scenario}: p2p == {other}", rel=0.0)
+                    assert_struct(plain(a["step_memory"]), plain(o_["step_memory"]), f"mem p2p == {other}", rel=0.0)
+                    assert_struct(plain(a["process"]), plain(o_["process"]), f"proc p2p == {other}", rel=0.0)
                 assert_struct(plain(a["step_memory"]["diagnosis"]), plain(b["step_memory"]["diagnosis"]), "mem p2p == nccl", rel=0.0)
                 if recs_all is not None:
                     ref = step_time_oracle.step_time_section(oracle_time_rows(recs_all, W), max_rows=W)
@@ -73,8 +86,8 @@ def main():
                     assert a["step_time"]["data"]["aligned_window"]["steps_analyzed"] == W
                 print(f"[multi_gpu_check] {scenario} R={world} W={W}: OK "
                       f"({a['step_time']['diagnosis']['primary']['status'] if a['step_time']['diagnosis'] else None}); "
-                      f"p2p {a['reduce'].timings_ms.get('total', 0):.3f} ms, nccl {b['reduce'].timings_ms.get('total', 0):.3f} ms, "
-                      f"a2a {c['reduce'].timings_ms.get('total', 0):.3f} ms")
+                      + ", ".join(f"{k} {v['_ms']:.3f} ms" for k, v in results.items())
+                      + f" (auto -> {results['auto']['reduce'].exchange})")
             except AssertionError as exc:
                 failures += 1
                 print(f"[multi_gpu_check] {scenario}: FAILED {exc}")

@@ -113,3 +113,25 @@ def test_replay_digest_is_stable():
     assert replay.replay_digest(a) != replay.replay_digest(replay.make_step_replay("ragged", 3, 50, seed=9))
     only = replay.make_step_replay("ragged", 3, 50, seed=8, only_ranks=[2])
     assert np.array_equal(only[2], a[2])
+
+
+def test_ctypes_mirrors_match_the_c_layouts():
+    """Every struct that crosses the ABI: sizeof in the library == sizeof of the ctypes mirror."""
+    from traceml_b200 import _abi
+
+    lib = _abi.lib()
+    pairs = {
+        "tml_step_record": _abi.StepRecord, "tml_proc_record": _abi.ProcRecord,
+        "tml_live_phase": _abi.LivePhase, "tml_live_stats": _abi.LiveStats,
+        "tml_win_info": _abi.WinInfo, "tml_align_info": _abi.AlignInfo,
+        "tml_reduce_args": _abi.ReduceArgs, "tml_band_args": _abi.BandArgs, "tml_band_out": _abi.BandOut,
+        "tml_proc_agg": _abi.ProcAgg, "tml_comm": _abi.Comm, "tml_reduce_run_args": _abi.ReduceRunArgs,
+        "tml_kind_result": _abi.KindResultC, "tml_reduce_run_out": _abi.ReduceRunOut,
+        "tml_combined_info": _abi.CombinedInfo, "tml_combined_align": _abi.CombinedAlign,
+        "tml_rank_means": _abi.RankMeans, "tml_trend_in": _abi.TrendIn, "tml_st_diag_in": _abi.StDiagIn,
+        "tml_mem_metric_in": _abi.MemMetricIn, "tml_mem_diag_in": _abi.MemDiagIn,
+        "tml_proc_diag_in": _abi.ProcDiagIn,
+    }
+    for name, cls in pairs.items():
+        assert int(lib.tml_struct_size(name.encode())) == C.sizeof(cls), name
+    assert int(lib.tml_struct_size(b"nope")) == 0

@@ -178,3 +178,71 @@ def test_large_window_properties(cuda):
     assert torch.equal(ser[8], torch.maximum(wall, comp))
     for e in engines:
         e.close()
+
+
+# ---------------------------------------------------------------------------- native sequencing
+@pytest.mark.parametrize("scenario,S,W,slots", [
+    ("balanced", 300, 10_000, None), ("wait_heavy", 300, 128, None), ("duplicates", 240, 10_000, None),
+    ("trend_worsening", 600, 10_000, None), ("mem_creep_confirmed", 300, 100, None),
+    ("cpu_only", 120, 10_000, None), ("balanced", 1000, 200, 300), ("warmup", 40, 10_000, None),
+])
+def test_native_driver_equals_python_driver(cuda, scenario, S, W, slots):
+    """tml_reduce_run (csrc/tml_summary.cpp) against the Python staging of the same C-ABI
+    stages, one rank: every section identical, bit for bit."""
+    from traceml_b200 import replay, sections
+    from traceml_b200.engine import Engine
+
+    recs = replay.make_step_replay(scenario, 1, S, seed=31)[0]
+    procs = replay.make_proc_replay("overhang", 1, 300, seed=31)[0]
+    out = {}
+    for native in (True, False):
+        e = Engine(device=0, rank=0, world=1, ring_slots=slots or max(64, S + 8), proc_slots=512)
+        e.load_steps(recs)
+        e.load_procs(procs)
+        torch.cuda.synchronize()
+        try:
+            se = sections.SummaryEngine([e], ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=1, native=native)
+            assert se.reducer._native_ok() == native
+            out[native] = se.build(W, W)
+            again = se.build(W, W)  # workspace reuse
+            again.pop("reduce")
+            first = dict(out[native]); first.pop("reduce")
+            assert_struct(plain(first), plain(again), "repeatable", rel=0.0)
+        finally:
+            e.close()
+    a, b = out[True], out[False]
+    ra, rb = a.pop("reduce"), b.pop("reduce")
+    assert_struct(plain(a), plain(b), "native == python", rel=0.0)
+    assert ra.exchange == rb.exchange == "local" and ra.fused_pass == rb.fused_pass
+    assert ra.time.n_common == rb.time.n_common and ra.mem.n_common == rb.mem.n_common
+    if ra.time.n_common:
+        assert torch.equal(ra.time.series[:12], rb.time.series[:12])
+    if ra.mem.n_common:
+        assert torch.equal(ra.mem.series[12:], rb.mem.series[12:])
+
+
+@pytest.mark.parametrize("name", ["single_rank", "single_rank_wait", "cpu_only_r1"])
+def test_native_driver_vs_reference_golden(cuda, name):
+    """The native driver against the reference's own outputs (one-rank goldens)."""
+    from helpers import load_golden
+    from traceml_b200 import replay, sections
+    from traceml_b200.engine import Engine
+
+    g = load_golden(name)
+    recs = step_replay_for(g)
+    e = Engine(device=0, rank=0, world=1, ring_slots=max(64, len(recs[0]) + 8), proc_slots=64)
+    e.load_steps(recs[0])
+    torch.cuda.synchronize()
+    try:
+        se = sections.SummaryEngine([e], ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=1)
+        assert se.reducer._native_ok()
+        got = se.build(g["window"], g["window"])
+    finally:
+        e.close()
+    ref = g["step_time"]
+    assert_struct(plain(got["step_time"]["data"]), ref["data"], "data")
+    assert_struct(plain(got["step_time"]["diagnosis"]), ref["diagnosis"], "diagnosis")
+    mref = g["step_memory"]
+    assert_struct(plain(got["step_memory"]["metrics"]), mref["metrics"], "mem.metrics")
+    assert_struct(strip_device(plain(got["step_memory"]["diagnosis"]))["primary"],
+                  strip_device(mref["diagnosis"])["primary"], "mem.primary")

@@ -90,6 +90,35 @@ class ProcAgg(C.Structure):
                 ("any_gpu_available", u32), ("sum_cpu_lo", f64)]
 
 
+class Comm(C.Structure):
+    _fields_ = [("nccl_comm", vp), ("rank", i32), ("world", i32)]
+
+
+XCHG = {"auto": 0, "p2p": 1, "a2a": 2}
+XCHG_NAME = {0: "auto", 1: "p2p", 2: "a2a", 3: "local"}
+
+
+class ReduceRunArgs(C.Structure):
+    _fields_ = [("window", u32), ("proc_rows", u32), ("exchange", u32), ("speculate", u32)]
+
+
+class KindResultC(C.Structure):
+    _fields_ = [("observed", u32), ("n_used", u32), ("used", i32 * TML_MAX_RANKS),
+                ("n_common", u64), ("start_step", u64), ("end_step", u64),
+                ("n_rows", u64 * TML_MAX_RANKS), ("t_sums", (f64 * 7) * TML_MAX_RANKS),
+                ("m_sums", (f64 * 4) * TML_MAX_RANKS), ("has_bands", u32), ("_pad", u32),
+                ("band_sum", (f64 * 3) * 16), ("band_cnt", (u64 * 3) * 16),
+                ("tail_first", f64 * 16), ("tail_last", f64 * 16),
+                ("shard_lo", u64), ("shard_hi", u64), ("series", vp)]
+
+
+class ReduceRunOut(C.Structure):
+    _fields_ = [("n_ranks", u32), ("exchange_used", u32), ("fused_pass", u32), ("n_exchanges", u32),
+                ("infos", WinInfo * TML_MAX_RANKS), ("procs", ProcAgg * TML_MAX_RANKS),
+                ("time", KindResultC), ("mem", KindResultC), ("k3a_ms", f64), ("k4_ms", f64),
+                ("stage_ms", f64 * 5)]
+
+
 class RankMeans(C.Structure):
     _fields_ = [("rank", i32), ("steps_analyzed", i64), ("dataloader_ms", f64), ("forward_ms", f64),
                 ("backward_ms", f64), ("optimizer_ms", f64), ("step_cpu_ms", f64)]
@@ -156,6 +185,8 @@ SIGNATURES = {
     "tml_peer_close": (C.c_int, [vp, vp]),
     "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),
     "tml_kernel_ms": (C.c_double, [vp, u32]),
+    "tml_struct_size": (u64, [C.c_char_p]),
+    "tml_reduce_run": (C.c_int, [vp, C.POINTER(Comm), C.POINTER(ReduceRunArgs), vp, C.POINTER(ReduceRunOut)]),
     "tml_combined_prepare": (C.c_int, [vp, u32, u32, vp, C.POINTER(CombinedInfo)]),
     "tml_combined_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
     "tml_combined_select": (C.c_int, [vp, u32, u64, u64, vp, u32, vp, C.POINTER(CombinedAlign)]),

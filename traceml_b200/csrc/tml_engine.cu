@@ -33,6 +33,7 @@
 #include <unordered_map>
 
 #include "../../include/traceml_b200.h"
+#include "tml_internal.h"
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -1167,6 +1168,14 @@ static int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+extern "C" int tml_set_error_(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
 #define CK(call)                                                                         \
   do {                                                                                   \
     cudaError_t e_ = (call);                                                             \
@@ -1232,9 +1241,11 @@ struct tml_ctx {
   void* h_stage = nullptr;       // pinned 4 KB result staging
   std::unordered_map<std::string, void*> peers;
   void* comb[2] = {nullptr, nullptr};  // live step-combined workspaces, per kind (tml_combined.cuh)
+  void* run_ws = nullptr;        // tml_reduce_run's workspace (tml_summary.cpp)
 };
 
 static void comb_free(tml_ctx* c);
+extern "C" void** tml_run_ws_slot_(tml_ctx* c) { return &c->run_ws; }
 
 static int grid_for(const tml_ctx* c, u64 work_items, int per_block) {
   u64 need = (work_items + per_block - 1) / per_block;
@@ -1315,6 +1326,7 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
   comb_free(c);
+  tml_run_ws_free_(c->run_ws);
   delete c;
   return TML_OK;
 }

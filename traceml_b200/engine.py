@@ -48,6 +48,7 @@ class Engine:
         self._commit = self._lib.tml_step_commit
         self._drain_buf = np.zeros(4096, dtype=STEP_RECORD_DTYPE)
         self._pdrain_buf = np.zeros(8192, dtype=PROC_RECORD_DTYPE)
+        self._run_out = _abi.ReduceRunOut()
 
     # ------------------------------------------------------------ lifecycle
     @property
@@ -203,6 +204,16 @@ class Engine:
         p = C.c_void_p()
         _abi.check(self._lib.tml_peer_open(self._h, handle[:64], C.byref(p)), "tml_peer_open")
         return int(p.value) + int.from_bytes(handle[64:72], "little")
+
+    def reduce_run(self, window: int, proc_rows: int, exchange: str, speculate: bool, comm_ptr: int,
+                   rank: int, world: int, stream: int = 0) -> _abi.ReduceRunOut:
+        """The whole staged reduce, sequenced natively (csrc/tml_summary.cpp)."""
+        comm = _abi.Comm(comm_ptr or None, int(rank), int(world))
+        args = _abi.ReduceRunArgs(int(window), int(proc_rows or 0), _abi.XCHG[exchange], 1 if speculate else 0)
+        out = self._run_out  # ~45 KB: reused, not reallocated per call
+        _abi.check(self._lib.tml_reduce_run(self._h, C.byref(comm), C.byref(args), stream, C.byref(out)),
+                   "tml_reduce_run")
+        return out
 
     def kernel_ms(self, which: int) -> float:
         """Device time of the last K3a (0) / K4 (1) launch, from the library's own events."""

@@ -66,6 +66,9 @@ class LocalComm:
     def barrier(self) -> None:
         return None
 
+    def nccl_comm_ptr(self, device) -> Optional[int]:
+        return None
+
 
 class TorchDistComm:
     """torch.distributed plumbing (NCCL over NVLink on the box, gloo in CPU tests)."""
@@ -76,6 +79,7 @@ class TorchDistComm:
         self._dist = dist
         self.group = group
         self.n_vec = 0  # small vector all-gathers issued (the latency-bound exchanges)
+        self._comm_ptr: Optional[int] = None
         self.world = dist.get_world_size(group)
         self.index = dist.get_rank(group)
 
@@ -83,6 +87,24 @@ class TorchDistComm:
         out: List[Any] = [None] * self.world
         self._dist.all_gather_object(out, obj, group=self.group)
         return out
+
+    def nccl_comm_ptr(self, device: torch.device) -> Optional[int]:
+        """The ncclComm_t torch.distributed already holds for this group and device (the
+        native reduce issues its collectives on it); None when there is none to borrow."""
+        if self._comm_ptr is not None:
+            return self._comm_ptr or None
+        self._comm_ptr = 0
+        try:
+            if device.type == "cuda" and self._dist.get_backend(self.group) == "nccl":
+                pg = self.group or self._dist.distributed_c10d._get_default_group()
+                be = pg._get_backend(device)
+                if not be._is_initialized():  # lazy communicator: one tiny collective creates it
+                    self._dist.all_reduce(torch.zeros(1, device=device), group=self.group)
+                    torch.cuda.synchronize(device)
+                self._comm_ptr = int(be._comm_ptr())
+        except Exception:  # noqa: BLE001 -- private torch API: fall back to the torch collectives
+            self._comm_ptr = 0
+        return self._comm_ptr or None
 
     def all_gather_vec(self, vec, device=None) -> List[List[float]]:
         """Fixed-length f64 vectors: one small all-gather, no pickling."""
@@ -194,8 +216,10 @@ class WindowReducer:
     """Sequences the reduce stages for the local engines of this process."""
 
     def __init__(self, engines: Sequence[Any], comm: Any = None, *, device: Optional[torch.device] = None,
-                 exchange: str = "auto", speculate: bool = True):
+                 exchange: str = "auto", speculate: bool = True, native: bool = True):
         self.speculate = speculate
+        self.native = native        # False: sequence the stages from Python (reference driver)
+        self.last_exchanges = 0
         self.engines = list(engines)
         self.comm = comm or LocalComm()
         self.device = device or torch.device("cuda", self.engines[0].device)
@@ -245,6 +269,8 @@ class WindowReducer:
         window = max(1, int(window))
         dev = self.device
         stream = _stream_of(dev)
+        if self._native_ok() and not stage_timings:
+            return self._reduce_native(window, proc_rows, stream)
         self._k4_events = []
         self._timed = bool(stage_timings)
         R = self.comm.world * self.L
@@ -373,6 +399,66 @@ class WindowReducer:
                                           if hasattr(e, "kernel_ms")))
         return ReduceOutput(window=window, ranks=ranks, infos=infos, time=t_res, mem=m_res,
                             exchange=mode, fused_pass=same, timings_ms=timings, proc_aggs=proc_aggs)
+
+    # ------------------------------------------------------------------ native sequencing
+    def _native_ok(self) -> bool:
+        """One rank per process on a CUDA device: csrc/tml_summary.cpp runs the stages and
+        the collectives itself (on torch.distributed's own communicator)."""
+        if not self.native or self.L != 1 or self.device.type != "cuda":
+            return False
+        if not hasattr(self.engines[0], "reduce_run") or self.exchange == "nccl":
+            return False
+        if self.comm.world == 1:
+            return True
+        return bool(getattr(self.comm, "nccl_comm_ptr", lambda d: None)(self.device))
+
+    def _reduce_native(self, window: int, proc_rows: Optional[int], stream: int) -> ReduceOutput:
+        eng = self.engines[0]
+        world = self.comm.world
+        ptr = self.comm.nccl_comm_ptr(self.device) if world > 1 else 0
+        o = eng.reduce_run(window, int(proc_rows or 0), self.exchange if self.exchange in _abi.XCHG else "auto",
+                           self.speculate, ptr or 0, self.comm.index, world, stream)
+        R = int(o.n_ranks)
+        infos = {r: self._info_dict(o.infos[r]) for r in range(R)}
+        proc_aggs: Dict[int, Dict[str, Any]] = {}
+        if proc_rows:
+            for r in range(R):
+                pa = {f: getattr(o.procs[r], f) for f in _PROC_FIELDS}
+                for f in _PROC_INT_FIELDS:
+                    pa[f] = int(pa[f])
+                proc_aggs[r] = pa
+
+        def kind(k) -> KindResult:
+            res = KindResult(observed=int(k.observed), n_common=int(k.n_common))
+            for i in range(int(k.n_used)):
+                r = int(k.used[i])
+                res.windows[r] = RankWindow(rank=r, n_rows=int(k.n_rows[i]), t_sums=list(k.t_sums[i]),
+                                            m_sums=list(k.m_sums[i]), info=infos[r])
+            res.used = sorted(res.windows)
+            if res.windows:
+                res.start_step, res.end_step = int(k.start_step), int(k.end_step)
+            n = int(k.n_common)
+            if k.has_bands:
+                res.band_sum = [list(k.band_sum[s]) for s in range(16)]
+                res.band_cnt = [[int(c) for c in k.band_cnt[s]] for s in range(16)]
+                res.tail_first, res.tail_last = list(k.tail_first), list(k.tail_last)
+                res._lay = (trend_layout(n, min_points=200, warmup_frac=0.10),
+                            trend_layout(n, min_points=50, warmup_frac=0.0))
+            if k.series and n:
+                from .engine import _DevView
+                res.series = torch.as_tensor(_DevView(int(k.series), _abi.TML_SERIES_PER_STEP * n),
+                                             device=self.device).view(_abi.TML_SERIES_PER_STEP, n)
+            res.shard = (int(k.shard_lo), int(k.shard_hi))
+            return res
+
+        names = ("prepare", "align", "reduce", "bands", "total")
+        timings = {"host_" + nm: float(o.stage_ms[i]) for i, nm in enumerate(names)}
+        timings.update({nm: float(o.stage_ms[i]) for i, nm in enumerate(names)})  # stages end in a sync
+        timings["k3a"], timings["k4"] = float(o.k3a_ms), max(0.0, float(o.k4_ms))
+        self.last_exchanges = int(o.n_exchanges)
+        return ReduceOutput(window=window, ranks=list(range(R)), infos=infos, time=kind(o.time), mem=kind(o.mem),
+                            exchange=_abi.XCHG_NAME[int(o.exchange_used)], fused_pass=bool(o.fused_pass),
+                            timings_ms=timings, proc_aggs=proc_aggs)
 
     # ------------------------------------------------------------------ alignment
     def _spec_len(self) -> int:

@@ -267,8 +267,8 @@ class SummaryEngine:
     """All three sections for the local engines of this process."""
 
     def __init__(self, engines, comm=None, *, exchange: str = "auto",
-                 ram_total: Optional[float] = None, gpu_count: Optional[int] = None):
-        self.reducer = WindowReducer(engines, comm, exchange=exchange)
+                 ram_total: Optional[float] = None, gpu_count: Optional[int] = None, native: bool = True):
+        self.reducer = WindowReducer(engines, comm, exchange=exchange, native=native)
         self.engines = list(engines)
         self.comm = self.reducer.comm
         if ram_total is None:
@@ -302,6 +302,8 @@ class SummaryEngine:
         # the process rules need only the first exchange: they run under the K4 launch
         out = self.reducer.reduce(window, proc_rows=max(1, int(proc_rows)), overlap=_process,
                                   stage_timings=timings)
+        if "aggs" not in box:  # native sequencing: no host window between the stages
+            _process(out.proc_aggs)
         aggs = box["aggs"]
         with_gpu = [a for a in aggs.values() if a["n_gpu"] > 0]
         gpu_total = max((a["max_total"] for a in with_gpu), default=None)
