@@ -339,8 +339,9 @@ typedef struct tml_proc_agg {
  * the SQL aggregates of reporting/sections/process/loader.py:56-230. */
 int tml_proc_reduce(tml_ctx* ctx, uint32_t max_rows, void* stream,
                     tml_proc_agg* out);
-/* Split form: launch without synchronising; collect after any later
- * synchronisation of the same stream (tml_win_prepare provides one). */
+/* Split form: launch without synchronising; collect waits (on an event) only if
+ * the results have not landed yet -- normally a later synchronisation of the same
+ * stream (tml_win_prepare's) has already covered it. */
 int tml_proc_reduce_launch(tml_ctx* ctx, uint32_t max_rows, void* stream);
 int tml_proc_reduce_collect(tml_ctx* ctx, tml_proc_agg* out);
 

@@ -241,12 +241,18 @@ def check(status: int, what: str = "") -> int:
     return status
 
 
+_DIAG_BUF = None
+
+
 def diag_json(fn_name: str, arg: C.Structure, cap: int = 1 << 16) -> Any:
     """Run one of the tml_diag_* engines and parse its JSON."""
+    global _DIAG_BUF
     l = lib()
-    buf = C.create_string_buffer(cap)
-    rc = getattr(l, fn_name)(C.byref(arg), buf, cap)
+    if _DIAG_BUF is None or len(_DIAG_BUF) < cap:
+        _DIAG_BUF = C.create_string_buffer(cap)
+    buf = _DIAG_BUF
+    rc = getattr(l, fn_name)(C.byref(arg), buf, len(buf))
     if rc == -8:  # TML_ERR_SMALL
-        return diag_json(fn_name, arg, cap * 8)
+        return diag_json(fn_name, arg, len(buf) * 8)
     check(rc, fn_name)
-    return json.loads(buf.value.decode("utf-8"))
+    return json.loads(buf.value)

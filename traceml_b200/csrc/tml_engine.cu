@@ -1197,6 +1197,7 @@ struct tml_ctx {
   // host-side step state (training thread)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of k_window_rows alone
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // device time of k_window_reduce alone
+  cudaEvent_t ev_proc = nullptr;             // the process aggregates have reached the staging slot
   u64 commits = 0;
   u64 launches = 0;  // kernels this context has launched (bench: gpu_launches)
   u32 next_slot = 0;
@@ -1964,6 +1965,8 @@ int tml_proc_reduce_launch(tml_ctx* c, uint32_t max_rows, void* stream) {
   c->launches += 3;
   CK(cudaMemcpyAsync((char*)c->h_stage + 3072, c->d_pfinal, PR_COLS * sizeof(double),
                      cudaMemcpyDeviceToHost, s));
+  if (!c->ev_proc) CK(cudaEventCreateWithFlags(&c->ev_proc, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->ev_proc, s));
   return TML_OK;
 }
 
@@ -1975,6 +1978,9 @@ int tml_proc_reduce_collect(tml_ctx* c, tml_proc_agg* out) {
   out->max_ratio = -1.0;
   const u64 n = c->proc_pending_n;
   if (n == 0) return TML_OK;
+  // normally complete already (tml_win_prepare synchronised the stream); an empty step
+  // ring returns from there without a sync, so wait on the copy itself
+  CK(cudaEventSynchronize(c->ev_proc));
   double f[PR_COLS];
   memcpy(f, (char*)c->h_stage + 3072, sizeof(f));
   out->n = n;

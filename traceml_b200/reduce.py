@@ -432,16 +432,16 @@ class WindowReducer:
             res = KindResult(observed=int(k.observed), n_common=int(k.n_common))
             for i in range(int(k.n_used)):
                 r = int(k.used[i])
-                res.windows[r] = RankWindow(rank=r, n_rows=int(k.n_rows[i]), t_sums=list(k.t_sums[i]),
-                                            m_sums=list(k.m_sums[i]), info=infos[r])
+                res.windows[r] = RankWindow(rank=r, n_rows=int(k.n_rows[i]), t_sums=k.t_sums[i][:],
+                                            m_sums=k.m_sums[i][:], info=infos[r])
             res.used = sorted(res.windows)
             if res.windows:
                 res.start_step, res.end_step = int(k.start_step), int(k.end_step)
             n = int(k.n_common)
             if k.has_bands:
-                res.band_sum = [list(k.band_sum[s]) for s in range(16)]
-                res.band_cnt = [[int(c) for c in k.band_cnt[s]] for s in range(16)]
-                res.tail_first, res.tail_last = list(k.tail_first), list(k.tail_last)
+                res.band_sum = [k.band_sum[s][:] for s in range(16)]
+                res.band_cnt = [k.band_cnt[s][:] for s in range(16)]
+                res.tail_first, res.tail_last = k.tail_first[:], k.tail_last[:]
                 res._lay = (trend_layout(n, min_points=200, warmup_frac=0.10),
                             trend_layout(n, min_points=50, warmup_frac=0.0))
             if k.series and n:
