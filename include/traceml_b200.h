@@ -542,6 +542,26 @@ typedef struct tml_proc_diag_in {
  * diagnostics/process/context.py:242-340, rules.py:71-345, api.py:84-118. */
 int tml_diag_process(const tml_proc_diag_in* in, char* json_out, size_t cap);
 
+/* ---------------------------------------------------------------- SECTIONS
+ * All three sections of one tml_reduce_run as one JSON object
+ * {"step_time": {data, diagnosis, global, overview}, "step_memory": {...},
+ *  "process": {...}}: per-rank RankStepSummary rows, aligned window, public
+ * rollups (reporting/sections/step_time/model.py:77-120,270-498,
+ * step_memory/model.py:224-246,322-412) and the three tml_diag_* results --
+ * what StepTimeSummarySection / StepMemorySummarySection / ProcessSummarySection
+ * hand to their kept payload builders
+ * (reporting/sections/{step_time,step_memory,process}/__init__.py:50-112).   */
+typedef struct tml_sections_args {
+  double ram_total;   /* psutil.virtual_memory().total (single node: per-host constant) */
+  int32_t gpu_count;  /* torch.cuda.device_count()                                      */
+  uint32_t window;
+  uint32_t proc_rows; /* 0: no process aggregates were collected                        */
+  uint32_t _pad;
+} tml_sections_args;
+
+int tml_sections_json(const tml_reduce_run_out* run, const tml_sections_args* args,
+                      char* json_out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,10 @@ class ReduceRunOut(C.Structure):
                 ("stage_ms", f64 * 5)]
 
 
+class SectionsArgs(C.Structure):
+    _fields_ = [("ram_total", f64), ("gpu_count", i32), ("window", u32), ("proc_rows", u32), ("_pad", u32)]
+
+
 class RankMeans(C.Structure):
     _fields_ = [("rank", i32), ("steps_analyzed", i64), ("dataloader_ms", f64), ("forward_ms", f64),
                 ("backward_ms", f64), ("optimizer_ms", f64), ("step_cpu_ms", f64)]
@@ -186,6 +190,7 @@ SIGNATURES = {
     "tml_win_reduce": (C.c_int, [vp, C.POINTER(ReduceArgs), vp]),
     "tml_kernel_ms": (C.c_double, [vp, u32]),
     "tml_struct_size": (u64, [C.c_char_p]),
+    "tml_sections_json": (C.c_int, [C.POINTER(ReduceRunOut), C.POINTER(SectionsArgs), vp, C.c_size_t]),
     "tml_reduce_run": (C.c_int, [vp, C.POINTER(Comm), C.POINTER(ReduceRunArgs), vp, C.POINTER(ReduceRunOut)]),
     "tml_combined_prepare": (C.c_int, [vp, u32, u32, vp, C.POINTER(CombinedInfo)]),
     "tml_combined_presence": (C.c_int, [vp, u32, u64, u64, vp, vp]),
@@ -256,3 +261,24 @@ def diag_json(fn_name: str, arg: C.Structure, cap: int = 1 << 16) -> Any:
         return diag_json(fn_name, arg, len(buf) * 8)
     check(rc, fn_name)
     return json.loads(buf.value)
+
+
+_SEC_BUF = None
+
+
+def sections_json(run_out, ram_total: float, gpu_count: int, window: int, proc_rows: int) -> Any:
+    """tml_sections_json -> dict; rank-keyed step-time tables get their int keys back."""
+    global _SEC_BUF
+    if _SEC_BUF is None:
+        _SEC_BUF = C.create_string_buffer(1 << 18)
+    args = SectionsArgs(float(ram_total), int(gpu_count), int(window), int(proc_rows or 0), 0)
+    rc = lib().tml_sections_json(C.byref(run_out), C.byref(args), _SEC_BUF, len(_SEC_BUF))
+    if rc == -8:  # TML_ERR_SMALL
+        _SEC_BUF = C.create_string_buffer(len(_SEC_BUF) * 8)
+        return sections_json(run_out, ram_total, gpu_count, window, proc_rows)
+    check(rc, "tml_sections_json")
+    res = json.loads(_SEC_BUF.value)
+    data = res["step_time"]["data"]
+    for key in ("aligned_summary", "per_global_rank_summary"):
+        data[key] = {int(k): v for k, v in data[key].items()}
+    return res

@@ -215,6 +215,10 @@ class Engine:
                    "tml_reduce_run")
         return out
 
+    def sections_json(self, run_out, ram_total: float, gpu_count: int, window: int, proc_rows: int):
+        """Step-Time / Step-Memory / Process sections of a reduce_run, parsed (csrc/tml_sections.cpp)."""
+        return _abi.sections_json(run_out, ram_total, gpu_count, window, proc_rows)
+
     def kernel_ms(self, which: int) -> float:
         """Device time of the last K3a (0) / K4 (1) launch, from the library's own events."""
         return float(self._lib.tml_kernel_ms(self._h, int(which)))

@@ -211,6 +211,34 @@ class ReduceOutput:
     proc_aggs: Dict[int, Dict[str, Any]] = field(default_factory=dict)
 
 
+class NativeReduceOutput:
+    """What ``SummaryEngine.build`` returns as ``"reduce"`` on the native path: the cheap
+    facts eagerly, the full ``ReduceOutput`` (per-rank windows, band sums, series view) only
+    if somebody asks -- the sections no longer need it."""
+
+    def __init__(self, reducer: "WindowReducer", o, window: int, proc_rows: Optional[int]):
+        self.window = window
+        self.exchange = _abi.XCHG_NAME[int(o.exchange_used)]
+        self.fused_pass = bool(o.fused_pass)
+        self.timings_ms = reducer.native_timings(o)
+        self.n_exchanges = int(o.n_exchanges)
+        self.ranks = list(range(int(o.n_ranks)))
+        self._snap = type(o).from_buffer_copy(o)  # the engine reuses its result struct
+        self._args = (reducer, window, proc_rows)
+        self._full: Optional[ReduceOutput] = None
+
+    def _get(self) -> ReduceOutput:
+        if self._full is None:
+            reducer, window, proc_rows = self._args
+            self._full = reducer.convert_native(self._snap, window, proc_rows)
+        return self._full
+
+    time = property(lambda self: self._get().time)
+    mem = property(lambda self: self._get().mem)
+    infos = property(lambda self: self._get().infos)
+    proc_aggs = property(lambda self: self._get().proc_aggs)
+
+
 # ----------------------------------------------------------------------------- reducer
 class WindowReducer:
     """Sequences the reduce stages for the local engines of this process."""
@@ -412,12 +440,27 @@ class WindowReducer:
             return True
         return bool(getattr(self.comm, "nccl_comm_ptr", lambda d: None)(self.device))
 
-    def _reduce_native(self, window: int, proc_rows: Optional[int], stream: int) -> ReduceOutput:
+    def run_native(self, window: int, proc_rows: Optional[int], stream: Optional[int] = None):
+        """tml_reduce_run on this process's engine; the raw result struct (valid until the next run)."""
         eng = self.engines[0]
         world = self.comm.world
         ptr = self.comm.nccl_comm_ptr(self.device) if world > 1 else 0
-        o = eng.reduce_run(window, int(proc_rows or 0), self.exchange if self.exchange in _abi.XCHG else "auto",
-                           self.speculate, ptr or 0, self.comm.index, world, stream)
+        return eng.reduce_run(window, int(proc_rows or 0), self.exchange if self.exchange in _abi.XCHG else "auto",
+                              self.speculate, ptr or 0, self.comm.index, world,
+                              _stream_of(self.device) if stream is None else stream)
+
+    def _reduce_native(self, window: int, proc_rows: Optional[int], stream: int) -> ReduceOutput:
+        return self.convert_native(self.run_native(window, proc_rows, stream), window, proc_rows)
+
+    @staticmethod
+    def native_timings(o) -> Dict[str, float]:
+        names = ("prepare", "align", "reduce", "bands", "total")
+        t = {"host_" + nm: float(o.stage_ms[i]) for i, nm in enumerate(names)}
+        t.update({nm: float(o.stage_ms[i]) for i, nm in enumerate(names)})  # stages end in a sync
+        t["k3a"], t["k4"] = float(o.k3a_ms), max(0.0, float(o.k4_ms))
+        return t
+
+    def convert_native(self, o, window: int, proc_rows: Optional[int]) -> ReduceOutput:
         R = int(o.n_ranks)
         infos = {r: self._info_dict(o.infos[r]) for r in range(R)}
         proc_aggs: Dict[int, Dict[str, Any]] = {}
@@ -451,10 +494,7 @@ class WindowReducer:
             res.shard = (int(k.shard_lo), int(k.shard_hi))
             return res
 
-        names = ("prepare", "align", "reduce", "bands", "total")
-        timings = {"host_" + nm: float(o.stage_ms[i]) for i, nm in enumerate(names)}
-        timings.update({nm: float(o.stage_ms[i]) for i, nm in enumerate(names)})  # stages end in a sync
-        timings["k3a"], timings["k4"] = float(o.k3a_ms), max(0.0, float(o.k4_ms))
+        timings = self.native_timings(o)
         self.last_exchanges = int(o.n_exchanges)
         return ReduceOutput(window=window, ranks=list(range(R)), infos=infos, time=kind(o.time), mem=kind(o.mem),
                             exchange=_abi.XCHG_NAME[int(o.exchange_used)], fused_pass=bool(o.fused_pass),

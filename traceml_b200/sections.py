@@ -285,6 +285,16 @@ class SummaryEngine:
         import torch
 
         gpu_count = self.gpu_count if self.gpu_count is not None else torch.cuda.device_count()
+        if self.reducer._native_ok() and not timings:
+            # one rank per process: stages, exchanges, rule engines and the section objects are
+            # all native (csrc/tml_summary.cpp, tml_sections.cpp); the host parses one JSON
+            from .reduce import NativeReduceOutput
+
+            rows = max(1, int(proc_rows))
+            o = self.reducer.run_native(max(1, int(window)), rows)
+            res = self.engines[0].sections_json(o, self.ram_total, gpu_count, max(1, int(window)), rows)
+            res["reduce"] = NativeReduceOutput(self.reducer, o, max(1, int(window)), rows)
+            return res
         box: Dict[str, Any] = {}
 
         def _process(proc_aggs):
