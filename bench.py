@@ -492,12 +492,14 @@ def main():
                           "GBps": k3a_bytes / (med["k3a"] * 1e-3) / 1e9 if med.get("k3a") else None},
     }
     if R > 1 and med.get("k4"):
-        # step-sharded K4 loads (R-1)/R of its rows from peer HBM: NVLink 5 (900 GB/s per
-        # direction per GPU, B200_PROFILING.md) is its bound, not the local HBM
+        # step-sharded K4 loads (R-1)/R of its rows from peer HBM: NVLink 5 is its bound, not the
+        # local HBM.  Denominator: the measured peer copy of 770 GB/s per direction per GPU
+        # (B200_PROFILING.md; 900 nominal)
         nv = (R - 1) * n_shard * 64.0
         kernels["k_window_reduce"]["nvlink"] = {
-            "bytes_in": nv, "GBps": nv / (med["k4"] * 1e-3) / 1e9, "peak": 900.0,
-            "frac": nv / (med["k4"] * 1e-3) / 1e9 / 900.0}
+            "bytes_in": nv, "GBps": nv / (med["k4"] * 1e-3) / 1e9, "peak": 770.0, "nominal": 900.0,
+            "frac": nv / (med["k4"] * 1e-3) / 1e9 / 770.0,
+            "peak_source": "measured peer copy, B200_PROFILING.md"}
     dom = max(kernels, key=lambda k: kernels[k]["ms"] or 0.0)
     traffic = None
     try:  # DRAM traffic per launch from the committed ncu capture, if it is this workload
@@ -528,7 +530,10 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, device) / args.steps
     barrier(world)
     e2e = {"value": b_reduce(R, W) / e2e_s / 1e9, "unit": "GB/s",
-           "h2d_bytes_per_step": (W * 128 + 60_000 * 64) * R, "d2h_bytes_per_step": 2_200 * R,
+           "h2d_bytes_per_step": (W * 128 + 60_000 * 64) * R,
+           # per rank: prepare results 616 B + process aggregates 128 B + band sums 1024 B, and at
+           # R > 1 the gathered exchange vectors (64 + 128 doubles per rank, read back on every rank)
+           "d2h_bytes_per_step": (1_768 + (1_536 * R if R > 1 else 0)) * R,
            "ms_per_step": e2e_s * 1e3}
 
     # ---- (3) per-step overhead leg
