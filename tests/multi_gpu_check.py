@@ -30,7 +30,9 @@ def main():
     from traceml_b200.reduce import TorchDistComm
 
     failures = 0
-    for scenario, S, W in (("straggler", 700, 10_000), ("ragged", 900, 256), ("input_straggler", 200_000, 150_000)):
+    for scenario, S, W in (("straggler", 700, 10_000), ("ragged", 900, 256), ("empty_rank", 300, 10_000),
+                           ("no_overlap", 120, 10_000), ("duplicates", 400, 100),
+                           ("input_straggler", 200_000, 150_000)):
         recs_all = replay.make_step_replay(scenario, world, S, seed=11) if S <= 1000 else None
         mine = (recs_all[rank] if recs_all is not None else
                 replay.make_step_replay(scenario, world, S, seed=11, only_ranks=[rank])[rank])
