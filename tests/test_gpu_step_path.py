@@ -47,12 +47,18 @@ def test_stamp_matches_cuda_events(cuda):
     assert list(recs["step"]) == list(range(1, 33))
     assert list(recs["peak_alloc"]) == [1000 + i for i in range(1, 33)]
     assert (recs["n_calls"][:, 2] == 1).all() and (recs["gpu_mask"] == 4).all()
+    diffs, outliers = [], 0
     for (e0, e1), r in zip(evs, recs):
         ev_us = e0.elapsed_time(e1) * 1000.0
         k_us = float(r["dur_ns"][2]) / 1000.0
         # the event pair brackets the stamp pair, so it can only be (slightly) longer
         assert k_us <= ev_us + 2.0
-        assert abs(ev_us - k_us) <= 2.0 + 0.01 * ev_us + 12.0, (ev_us, k_us)
+        diffs.append(ev_us - k_us)
+        if abs(ev_us - k_us) > 2.0 + 0.01 * ev_us + 12.0:
+            outliers += 1  # host descheduled between e0.record() and the begin stamp: the GPU idles
+    # in that gap, inside the event pair but before the stamp -- physical, not a stamp error
+    assert outliers <= 2, diffs
+    assert sorted(diffs)[len(diffs) // 2] <= 10.0, diffs
     eng.close()
 
 
