@@ -84,4 +84,157 @@ class ProcessProbe:
                            int(self.cores), int(self._stream.cuda_stream))
 
 
-__all__ = ["drain_to_wire", "ProcessProbe"]
+# ----------------------------------------------------------------------------- sampler seam
+class TableStore:
+    """The table contract of ``database/database.py:7-186``: bounded ``deque(maxlen=3000)``
+    per table plus a monotonic append counter, so the kept incremental sender can find the
+    new rows in O(1)."""
+
+    DEFAULT_MAX_ROWS = 3000
+
+    def __init__(self, sampler_name: str, max_rows: Optional[int] = None):
+        from collections import deque
+
+        self.sampler_name = sampler_name
+        self.max_rows = int(max_rows) if max_rows is not None else self.DEFAULT_MAX_ROWS
+        if self.max_rows <= 0:
+            raise ValueError(f"max_rows must be > 0, got {max_rows}")
+        self._deque = deque
+        self._tables: Dict[str, Any] = {}
+        self._append_count: Dict[str, int] = {}
+
+    def create_or_get_table(self, name: str):
+        if name not in self._tables:
+            self._tables[name] = self._deque(maxlen=self.max_rows)
+            self._append_count[name] = 0
+        return self._tables[name]
+
+    def add_record(self, table: str, row: Any) -> None:
+        self.create_or_get_table(table).append(row)
+        self._append_count[table] += 1
+
+    def all_tables(self) -> Dict[str, Any]:
+        return self._tables
+
+    def get_append_count(self, table: str) -> int:
+        return self._append_count.get(table, 0)
+
+
+def _identity_fields() -> Dict[str, Any]:
+    """database/database_sender.py:49-66 envelope identity, from the launcher's env contract."""
+    import socket
+
+    rank = int(os.environ.get("RANK", "0") or 0)
+    return {
+        "rank": rank, "global_rank": rank,
+        "local_rank": int(os.environ.get("LOCAL_RANK", "0") or 0),
+        "world_size": int(os.environ.get("WORLD_SIZE", "1") or 1),
+        "local_world_size": int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1),
+        "node_rank": int(os.environ.get("GROUP_RANK", os.environ.get("NODE_RANK", "0")) or 0),
+        "hostname": socket.gethostname(), "pid": os.getpid(),
+    }
+
+
+class RecordTap:
+    """One drain cursor per engine, fanned out: the step-time and step-memory samplers read
+    the same 128-B records."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.pending: Dict[str, List[Any]] = {"step_time": [], "step_memory": [], "process": []}
+        self.dropped = 0
+
+    def pump(self) -> None:
+        out = drain_to_wire(self.engine)
+        self.dropped += out["dropped"]
+        for k in self.pending:
+            self.pending[k].extend(out[k])
+
+    def take(self, kind: str) -> List[Any]:
+        rows, self.pending[kind] = self.pending[kind], []
+        return rows
+
+
+class _TapSampler:
+    """``BaseSampler`` contract (samplers/base_sampler.py:23-83): ``sampler_name``,
+    ``table_name``, ``db``, ``sample()`` that never raises, and ``collect_payload()`` with the
+    sender's envelope (database/database_sender.py:127-170)."""
+
+    sampler_name = ""
+    table_name = ""
+    kind = ""
+
+    def __init__(self, tap: RecordTap, max_rows_per_flush: int = -1):
+        self.tap = tap
+        self.db = TableStore(self.sampler_name)
+        self.max_rows_per_flush = int(max_rows_per_flush)
+        self.enable_send = True
+        self._last_sent: Dict[str, int] = {}
+
+    def sample(self) -> None:
+        try:
+            self.tap.pump()
+            for row in self.tap.take(self.kind):
+                self.db.add_record(self.table_name, row)
+        except Exception as exc:  # noqa: BLE001 -- samplers never interfere with training
+            import sys
+
+            print(f"[TraceML] {self.sampler_name}.sample failed: {exc}", file=sys.stderr)
+
+    def collect_payload(self) -> Optional[Dict[str, Any]]:
+        tables: Dict[str, List[Any]] = {}
+        for name, rows in self.db.all_tables().items():
+            total = self.db.get_append_count(name)
+            new = total - self._last_sent.get(name, 0)
+            if not rows or new <= 0:
+                continue
+            if self.max_rows_per_flush != -1:
+                new = min(new, self.max_rows_per_flush)
+            n = len(rows)
+            tables[name] = list(rows) if new >= n else [rows[i] for i in range(n - new, n)]
+            self._last_sent[name] = total
+        if not tables:
+            return None
+        return {**_identity_fields(), "sampler": self.sampler_name, "timestamp": time.time(), "tables": tables}
+
+
+class StepTimeSampler(_TapSampler):
+    """samplers/step_time_sampler.py:21-128 -- a drain of finished records, no event queries."""
+    sampler_name, table_name, kind = "StepTimeSampler", "StepTimeTable", "step_time"
+
+
+class StepMemorySampler(_TapSampler):
+    """samplers/step_memory_sampler.py:12-65."""
+    sampler_name, table_name, kind = "StepMemorySampler", "step_memory", "step_memory"
+
+
+class ProcessSampler(_TapSampler):
+    """samplers/process_sampler.py:36-238 -- takes a sample (host CPU / RSS + allocator counters,
+    committed to the device ring), then publishes what the ring produced."""
+    sampler_name, table_name, kind = "ProcessSampler", "ProcessTable", "process"
+
+    def __init__(self, tap: RecordTap, max_rows_per_flush: int = -1, probe: Optional[ProcessProbe] = None):
+        super().__init__(tap, max_rows_per_flush)
+        self.probe = probe
+
+    def sample(self) -> None:
+        try:
+            if self.probe is None:
+                self.probe = ProcessProbe()
+            self.probe.sample(self.tap.engine)
+        except Exception as exc:  # noqa: BLE001
+            import sys
+
+            print(f"[TraceML] ProcessSampler probe failed: {exc}", file=sys.stderr)
+        super().sample()
+
+
+def build_samplers(engine) -> List[_TapSampler]:
+    """The per-rank sampler set of profile ``run`` that is on this path
+    (runtime/sampler_registry.py:131-160: process, step_time, step_memory)."""
+    tap = RecordTap(engine)
+    return [ProcessSampler(tap), StepTimeSampler(tap), StepMemorySampler(tap)]
+
+
+__all__ = ["drain_to_wire", "ProcessProbe", "TableStore", "RecordTap", "StepTimeSampler",
+           "StepMemorySampler", "ProcessSampler", "build_samplers"]
