@@ -47,6 +47,9 @@ S fmt(const char* f, ...) {
 }
 
 S jstr(const S& s) {
+  bool plain = true;
+  for (unsigned char ch : s) if (ch == '"' || ch == '\\' || ch < 0x20) { plain = false; break; }
+  if (plain) { S o; o.reserve(s.size() + 2); o += '"'; o += s; o += '"'; return o; }
   S o = "\"";
   for (unsigned char ch : s) {
     if (ch == '"') o += "\\\"";
@@ -74,13 +77,13 @@ S jopt_num(double v, bool has) { return has ? jnum(v) : JNULL; }
 struct Obj {
   S s = "{";
   bool first = true;
-  Obj& kv(const char* k, const S& v) {
-    if (!first) s += ",";
+  Obj& kv(const char* k, const S& v) {  // keys are identifiers: no escaping needed
+    if (!first) s += ',';
     first = false;
-    s += jstr(k) + ":" + v;
+    s += '"'; s += k; s += "\":"; s += v;
     return *this;
   }
-  S done() const { return s + "}"; }
+  S done() const { S o; o.reserve(s.size() + 1); o = s; o += '}'; return o; }
 };
 S jarr(const std::vector<S>& v) {
   S o = "[";

@@ -44,12 +44,12 @@ struct Obj {
   S s = "{";
   bool first = true;
   Obj& kv(const S& k, const S& v) {
-    if (!first) s += ",";
+    if (!first) s += ',';
     first = false;
-    s += "\"" + k + "\":" + v;
+    s += '"'; s += k; s += "\":"; s += v;
     return *this;
   }
-  S done() const { return s + "}"; }
+  S done() const { S o; o.reserve(s.size() + 1); o = s; o += '}'; return o; }
 };
 
 struct RankSummary {  // RankStepSummary

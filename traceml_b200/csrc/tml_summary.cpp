@@ -104,6 +104,8 @@ struct RunWs {
   char* d_zero_rows = nullptr;  // a2a: what a rank outside `used` sends
   u64 cap_zero_rows = 0;
   bool p2p_warm = false;  // peer mappings already open: peer loads cost nothing extra
+  cudaStream_t side = nullptr;  // process aggregates (K6) run beside K3a, not in front of it
+  cudaEvent_t side_gate = nullptr;  // side waits for what `stream` held at entry (ring loads)
 };
 
 int ensure_ws(tml_ctx* c, RunWs** out) {
@@ -114,6 +116,8 @@ int ensure_ws(tml_ctx* c, RunWs** out) {
     CKC(cudaMalloc(&w->d_recv, (size_t)TML_MAX_RANKS * XV * sizeof(double)));
     CKC(cudaHostAlloc(&w->h_send, XV * sizeof(double), cudaHostAllocDefault));
     CKC(cudaHostAlloc(&w->h_recv, (size_t)TML_MAX_RANKS * XV * sizeof(double), cudaHostAllocDefault));
+    CKC(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&w->side_gate, cudaEventDisableTiming));
     *slot = w;
   }
   *out = (RunWs*)*slot;
@@ -461,7 +465,13 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
   const double t0 = now_ms();
 
   // ---- stage 1: local window + bounds; process aggregates and the speculative alignment ride along
-  if (args->proc_rows) CKT(tml_proc_reduce_launch(c, args->proc_rows, r.s));
+  // K6 on the side stream: three tiny kernels that would otherwise sit in front of K3a;
+  // tml_proc_reduce_collect waits on their own event
+  if (args->proc_rows) {
+    CKC(cudaEventRecord(r.w->side_gate, r.s));
+    CKC(cudaStreamWaitEvent(r.w->side, r.w->side_gate, 0));
+    CKT(tml_proc_reduce_launch(c, args->proc_rows, r.w->side));
+  }
   tml_win_info info;
   CKT(tml_win_prepare(c, window, r.s, &info));
   tml_proc_agg pagg;
@@ -558,6 +568,8 @@ extern "C" void tml_run_ws_free_(void* p) {
   cudaFree(w->d_send); cudaFree(w->d_recv); cudaFreeHost(w->h_send); cudaFreeHost(w->h_recv);
   cudaFree(w->d_presence); cudaFree(w->d_series[0]); cudaFree(w->d_series[1]);
   cudaFree(w->d_recv_rows); cudaFree(w->d_zero_rows);
+  if (w->side) cudaStreamDestroy(w->side);
+  if (w->side_gate) cudaEventDestroy(w->side_gate);
   delete w;
 }
 
