@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -467,6 +468,7 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
   // ---- stage 1: local window + bounds; process aggregates and the speculative alignment ride along
   // K6 on the side stream: three tiny kernels that would otherwise sit in front of K3a;
   // tml_proc_reduce_collect waits on their own event
+  // (measured on one box, A/B: 0.523 vs 0.537 ms/step at N = 1)
   if (args->proc_rows) {
     CKC(cudaEventRecord(r.w->side_gate, r.s));
     CKC(cudaStreamWaitEvent(r.w->side, r.w->side_gate, 0));
