@@ -140,8 +140,14 @@ __global__ void __launch_bounds__(32) k_comb_sums(const tml_window_row* __restri
   if (cacc->inrange == 0) { out[lane] = 0.0; return; }
   const double* p = reinterpret_cast<const double*>(xrows) + lane;
   double acc = lane < 6 ? 0.0 : -INFINITY;
-  if (lane < 6) { for (u64 j = 0; j < keep; ++j) acc += p[j * 8]; }
-  else { for (u64 j = 0; j < keep; ++j) acc = fmax(acc, p[j * 8]); }
+  // the loads are independent of the chain: unrolled so eight are in flight per DADD run
+  if (lane < 6) {
+#pragma unroll 8
+    for (u64 j = 0; j < keep; ++j) acc += __ldg(&p[j * 8]);
+  } else {
+#pragma unroll 8
+    for (u64 j = 0; j < keep; ++j) acc = fmax(acc, __ldg(&p[j * 8]));
+  }
   out[lane] = acc;
 }
 

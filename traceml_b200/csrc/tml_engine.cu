@@ -818,43 +818,76 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
 
 #define TML_EXACT_SUM_MAX (1u << 17)
 
-__global__ void __launch_bounds__(32) k_seq_sums(const tml_window_row* __restrict__ rows,
-                                                 const u8* __restrict__ flags, u32 need,
-                                                 long long first, long long last, int aligned,
-                                                 const tml_window_row* __restrict__ xrows,
-                                                 const u32* __restrict__ noncontig,
-                                                 const u32* __restrict__ sel_rows,
-                                                 long long dense_first,
-                                                 double* __restrict__ out) {
-  const int lane = threadIdx.x;
-  double acc = 0.0;
+#define SQ_THREADS 256
+// Reference-order sums: the seven per-rank sums as ONE IEEE add after another, newest row
+// first, exactly like the reference's Python loop -- rank tie-breaks downstream are decided
+// on their last ulp.  The adds cannot be reordered, but everything else can be taken off
+// the chain: the block streams 256-row tiles into shared memory with cp.async (double
+// buffered), all 256 threads derive their row's seven addends in parallel, and lanes 0..6 of
+// warp 0 then do exactly one dependent DADD per row.  (ncu r01: the first version -- loads
+// and the derived values inside the serial loop -- took 394 ns/row, 3.9 ms at the default
+// W = 10^4: FP64 issue on this part is slow enough that the ~10 FP64 instructions per row,
+// executed by one warp under five-way divergence, dominated.)
+__global__ void __launch_bounds__(SQ_THREADS) k_seq_sums(const tml_window_row* __restrict__ rows,
+                                                         const u8* __restrict__ flags, u32 need,
+                                                         long long first, long long last, int aligned,
+                                                         const tml_window_row* __restrict__ xrows,
+                                                         const u32* __restrict__ noncontig,
+                                                         const u32* __restrict__ sel_rows,
+                                                         long long dense_first,
+                                                         double* __restrict__ out) {
+  __shared__ __align__(16) double raw[2][SQ_THREADS][8];
+  __shared__ __align__(16) double pre[SQ_THREADS][8];
+  const int tid = threadIdx.x;
   // aligned mode: the aligned rows are either the gathered copy or a contiguous slice
   if (aligned) {
     if (dense_first >= 0) rows = rows + dense_first;
     else rows = (*noncontig) ? xrows : (rows + sel_rows[0]);
   }
-  const double2* r2 = reinterpret_cast<const double2*>(rows);
-#pragma unroll 4
-  for (long long i = last; i >= first; --i) {
-    const double2 a = __ldg(&r2[i * 4 + 0]);  // dl, h2d
-    const double2 b = __ldg(&r2[i * 4 + 1]);  // fwd, bwd
-    const double2 c = __ldg(&r2[i * 4 + 2]);  // opt, wall
-    const bool use = flags ? ((flags[i] & need) == need) : true;
-    const double compute = (b.x + b.y) + c.x;
-    const double traced = fmax(c.y, compute);
-    double v;
-    switch (lane) {
-      case 0: v = a.x; break;
-      case 1: v = b.x; break;
-      case 2: v = b.y; break;
-      case 3: v = c.x; break;
-      case 4: v = aligned ? fmax(0.0, traced) : c.y; break;
-      case 5: v = traced; break;
-      default: v = a.x + traced; break;
+  const long long n = last - first + 1;
+  const long long ntiles = n > 0 ? (n + SQ_THREADS - 1) / SQ_THREADS : 0;
+  auto issue = [&](long long t, int buf) {  // tile t: rows last - t*256 - k, k = 0..255 (descending)
+    const long long i = last - t * SQ_THREADS - tid;
+    if (i >= first) {
+      const uint4* src = reinterpret_cast<const uint4*>(rows + i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cp_async16(&raw[buf][tid][q * 2], src + q);
     }
-    acc += use ? v : 0.0;  // + 0.0 leaves a non-negative running sum unchanged
+  };
+  double acc = 0.0;
+  if (ntiles) issue(0, 0);
+  cp_async_commit();
+  for (long long t = 0; t < ntiles; ++t) {
+    const int buf = (int)(t & 1);
+    if (t + 1 < ntiles) issue(t + 1, buf ^ 1);
+    cp_async_commit();
+    const long long i = last - t * SQ_THREADS - tid;
+    const bool live = i >= first;
+    const bool use = live && (flags ? ((flags[i] & need) == need) : true);
+    cp_async_wait<1>();  // this thread's part of tile t has landed
+    if (live) {          // a thread derives the addends of the row it fetched itself
+      const double* r = raw[buf][tid];
+      const double dl = r[0], fwd = r[2], bwd = r[3], opt = r[4], wall = r[5];
+      const double compute = (fwd + bwd) + opt;
+      const double traced = fmax(wall, compute);
+      double* o = pre[tid];
+      // + 0.0 leaves a non-negative running sum unchanged: unused rows add zeros
+      o[0] = use ? dl : 0.0; o[1] = use ? fwd : 0.0; o[2] = use ? bwd : 0.0; o[3] = use ? opt : 0.0;
+      o[4] = use ? (aligned ? fmax(0.0, traced) : wall) : 0.0;
+      o[5] = use ? traced : 0.0;
+      o[6] = use ? dl + traced : 0.0;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      const long long left = n - t * SQ_THREADS;
+      const int cnt = left < SQ_THREADS ? (int)left : SQ_THREADS;
+#pragma unroll 8
+      for (int k = 0; k < cnt; ++k) acc += pre[k][tid];  // the chain: one DADD per row
+    }
+    __syncthreads();  // pre and raw[buf] are free again
   }
-  if (lane < 7) out[lane] = acc;
+  cp_async_wait<0>();
+  if (tid < 7) out[tid] = acc;
 }
 
 // ------------------------------------------------------------------ K4: window reduce
@@ -1594,7 +1627,7 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   c->launches += 2;  // K3a + its finalize
   const bool exact_win = (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
   if (exact_win) {  // reference-order sums (used instead of the tree sums)
-    k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, c->d_flags, RF_USABLE | RF_IN_TIME, (long long)c->win_tstart,
+    k_seq_sums<<<1, SQ_THREADS, 0, s>>>(c->d_rows, c->d_flags, RF_USABLE | RF_IN_TIME, (long long)c->win_tstart,
                                 (long long)n - 1, 0, nullptr, nullptr, nullptr, -1ll, c->d_final);
     CK(cudaPeekAtLastError());
     c->launches += 1;
@@ -1720,7 +1753,7 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   c->launches += 2;
   const bool exact = (kind == TML_KIND_TIME) && keep <= TML_EXACT_SUM_MAX;
   if (exact) {
-    k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)keep - 1, 1, c->d_xrows[kind],
+    k_seq_sums<<<1, SQ_THREADS, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)keep - 1, 1, c->d_xrows[kind],
                                 c->d_noncontig, c->d_selrow, -1ll, c->d_final + 16);
     CK(cudaPeekAtLastError());
     c->launches += 1;
@@ -1790,7 +1823,7 @@ int tml_win_select_dense(tml_ctx* c, uint32_t kind, uint64_t first_step, uint64_
   const bool exact = (kind == TML_KIND_TIME) && n_common <= TML_EXACT_SUM_MAX;
   char* st = (char*)c->h_stage;
   if (exact) {
-    k_seq_sums<<<1, 32, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)n_common - 1, 1, nullptr, nullptr,
+    k_seq_sums<<<1, SQ_THREADS, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)n_common - 1, 1, nullptr, nullptr,
                                 nullptr, (long long)first_row, c->d_final + 16);
     CK(cudaPeekAtLastError());
     c->launches += 1;
