@@ -825,9 +825,8 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
 // the chain: the block streams 256-row tiles into shared memory with cp.async (double
 // buffered), all 256 threads derive their row's seven addends in parallel, and lanes 0..6 of
 // warp 0 then do exactly one dependent DADD per row.  (ncu r01: the first version -- loads
-// and the derived values inside the serial loop -- took 394 ns/row, 3.9 ms at the default
-// W = 10^4: FP64 issue on this part is slow enough that the ~10 FP64 instructions per row,
-// executed by one warp under five-way divergence, dominated.)
+// and the derived values inside the serial loop, one warp, five divergent paths per row --
+// took 394 ns/row, 3.9 ms at the default W = 10^4; this one takes 10 ns/row.)
 __global__ void __launch_bounds__(SQ_THREADS) k_seq_sums(const tml_window_row* __restrict__ rows,
                                                          const u8* __restrict__ flags, u32 need,
                                                          long long first, long long last, int aligned,
