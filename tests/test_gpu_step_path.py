@@ -351,3 +351,45 @@ def test_final_summary_public_api(cuda):
     else:              # kept builders available: the reference's own payload
         assert st["metadata"]["training_total_steps"] == 65
     assert "Step Time" in out["text"] or "Step Time:" in out["text"]
+
+
+def test_phases_side_by_side_with_the_reference_timer_path(cuda):
+    """SURVEY 8d, live-timer tolerance: the reference's timer path (oracle port: pooled CUDA
+    events resolved by the sampler) and this engine time the SAME regions of the same steps,
+    the reference's region nested outside ours.  Per GPU phase per step |d| <= 2 us + 1 %
+    (+ the event/stamp launch gap), and the means over >= 100 steps agree within 0.5 % + 2 us."""
+    from oracle.timer_oracle import ReferenceTimerPath
+    from traceml_b200.engine import Engine
+
+    ref = ReferenceTimerPath()
+    eng = Engine(device=0, ring_slots=512)
+    s = torch.cuda.current_stream().cuda_stream
+    model = torch.nn.Linear(8, 8).cuda()
+    names = {2: "_traceml_internal:forward_time", 3: "_traceml_internal:backward_time",
+             4: "_traceml_internal:optimizer_step"}
+    spin_ms = {2: 0.4, 3: 0.8, 4: 0.15}
+    N = 120
+    for step in range(1, N + 1):
+        with ref.trace_step(model):
+            for ph in (2, 3, 4):
+                with ref.timed_region(names[ph]):
+                    slot = eng.phase_begin(ph, s)
+                    _spin(spin_ms[ph] * (1.0 + 0.1 * (step % 3)))
+                    assert eng.phase_end(ph, slot, s) == 0
+        assert eng.step_commit(step, 0, 0, 0, time.time(), s) == 0
+    torch.cuda.synchronize()
+    rows = ref.sample()["step_time"]
+    recs, dropped = eng.drain()
+    assert dropped == 0 and len(recs) == N == len(rows)
+    assert [r["step"] for r in rows] == [int(x) for x in recs["step"]]
+    worst = 0.0
+    for ph in (2, 3, 4):
+        theirs = np.array([list(r["events"][names[ph]].values())[0]["duration_ms"] for r in rows]) * 1e3  # us
+        ours = recs["dur_ns"][:, ph].astype(np.float64) / 1e3
+        assert (ours <= theirs + 2.0).all()          # their events bracket our stamps
+        d = theirs - ours
+        worst = max(worst, float(np.max(d - 0.01 * theirs)))
+        assert np.sum(d > 2.0 + 0.01 * theirs + 12.0) <= 2, (ph, d.max())
+        assert abs(theirs.mean() - ours.mean()) <= 0.005 * theirs.mean() + 8.0, (ph, theirs.mean(), ours.mean())
+        assert (recs["n_calls"][:, ph] == 1).all()
+    eng.close()
