@@ -361,6 +361,17 @@ def oracle_reduce_sample(R: int, W: int, seed: int = 1):
     return once
 
 
+def workload_config(R: int, W: int) -> dict:
+    """The `config` both arms report: the workload is the same, the reference arm times a
+    bounded sample of it."""
+    return {"workload": f"BASELINE config 4 reduce-stress replay: R={R} ranks x W={W} step "
+                        "records/rank (128 B) + 60000 process samples/rank; full window "
+                        "reduce + diagnosis per step",
+            "window": W, "ranks": R,
+            "l2": "inputs larger than L2 (ring 512 MB/rank at W=4e6); no flush needed",
+            "algorithmic_bytes_per_step": b_reduce(R, W)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -377,8 +388,9 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"reduce-stress replay sample: R={R} ranks x W={Ws} steps (oracle port, "
-                               "rows already parsed: no SQLite/JSON)"},
+        "config": dict(workload_config(R, int(args.window)),
+                       sample=f"each step = R={R} ranks x {Ws} rows of that workload through the oracle port "
+                              "of the reference's Python reduce (rows already parsed: no SQLite/JSON)"),
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": "port",
                          "sample": f"R={R} x W={Ws} rows, median of {len(times)}; {t / (R * Ws) * 1e6:.1f} us/row"},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -560,12 +572,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"BASELINE config 4 reduce-stress replay: R={R} ranks x W={W} step "
-                                   "records/rank (128 B) + 60000 process samples/rank; full window "
-                                   "reduce + diagnosis per step",
-                       "window": W, "ranks": R, "exchange": res["reduce"].exchange,
-                       "l2": "inputs larger than L2 (ring 512 MB/rank at W=4e6); no flush needed",
-                       "algorithmic_bytes_per_step": b_reduce(R, W)},
+            "config": dict(workload_config(R, W), exchange=res["reduce"].exchange),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "records_per_s": R * W / (ms_step * 1e-3),
             "scaling_note": "weak: every rank holds W records; by the SURVEY formula the bytes grow as "
