@@ -45,14 +45,8 @@ class LocalComm:
     world = 1
     index = 0
 
-    def all_gather_obj(self, obj: Any) -> List[Any]:
-        return [obj]
-
     def all_gather_vec(self, vec, device=None) -> List[List[float]]:
         return [list(vec)]
-
-    def all_gather_bytes(self, blob: bytes, device=None) -> List[bytes]:
-        return [bytes(blob)]
 
     def all_reduce_min_(self, t: torch.Tensor) -> None:
         return None
@@ -83,11 +77,6 @@ class TorchDistComm:
         self.world = dist.get_world_size(group)
         self.index = dist.get_rank(group)
 
-    def all_gather_obj(self, obj: Any) -> List[Any]:
-        out: List[Any] = [None] * self.world
-        self._dist.all_gather_object(out, obj, group=self.group)
-        return out
-
     def nccl_comm_ptr(self, device: torch.device) -> Optional[int]:
         """The ncclComm_t torch.distributed already holds for this group and device (the
         native reduce issues its collectives on it); None when there is none to borrow."""
@@ -114,15 +103,6 @@ class TorchDistComm:
         out = torch.empty(self.world * inp.numel(), dtype=torch.float64, device=dev)
         self._dist.all_gather_into_tensor(out, inp, group=self.group)
         return out.view(self.world, -1).cpu().tolist()
-
-    def all_gather_bytes(self, blob: bytes, device=None) -> List[bytes]:
-        dev = device or torch.device("cpu")
-        inp = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
-        out = torch.empty(self.world * inp.numel(), dtype=torch.uint8, device=dev)
-        self._dist.all_gather_into_tensor(out, inp, group=self.group)
-        flat = out.cpu().numpy().tobytes()
-        n = len(blob)
-        return [flat[i * n:(i + 1) * n] for i in range(self.world)]
 
     def all_reduce_min_(self, t: torch.Tensor) -> None:
         self._dist.all_reduce(t, op=self._dist.ReduceOp.MIN, group=self.group)
@@ -253,7 +233,6 @@ class WindowReducer:
         self.device = device or torch.device("cuda", self.engines[0].device)
         self.L = len(self.engines)
         self.exchange = exchange
-        self._series_cache: Dict[int, torch.Tensor] = {}
         self._p2p_warm = False  # peer mappings already open: p2p costs nothing extra
         self._k4_events: List[Any] = []
 
@@ -287,8 +266,7 @@ class WindowReducer:
                 "lo": [i(v[8]), i(v[9])], "hi": [i(v[10]), i(v[11])],
                 "t_sums": [float(x) for x in v[12:19]], "t_count": i(v[19]), "n_both": i(v[20]), "dense": [i(v[21]), i(v[22])]}
 
-    def reduce(self, window: int, *, want_series: bool = False,
-               proc_rows: Optional[int] = None, overlap=None, stage_timings: bool = False) -> ReduceOutput:
+    def reduce(self, window: int, *, proc_rows: Optional[int] = None, overlap=None, stage_timings: bool = False) -> ReduceOutput:
         """``overlap(proc_aggs)``: host work that needs only the process aggregates; it
         runs after K4 has been launched and before the first wait on it.
         ``stage_timings``: per-stage CUDA-event / host-clock breakdown (a diagnostic: a dozen torch
