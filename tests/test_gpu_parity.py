@@ -246,3 +246,48 @@ def test_native_driver_vs_reference_golden(cuda, name):
     assert_struct(plain(got["step_memory"]["metrics"]), mref["metrics"], "mem.metrics")
     assert_struct(strip_device(plain(got["step_memory"]["diagnosis"]))["primary"],
                   strip_device(mref["diagnosis"])["primary"], "mem.primary")
+
+
+@pytest.mark.parametrize("R,scenario", [(11, "ragged"), (16, "compute_straggler")])
+def test_more_than_eight_ranks(cuda, R, scenario):
+    """R > 8 takes the generic (local-array, insertion-sort) reduce kernel and, in the live
+    tick, numpy's blocked pairwise order for the per-step sums: both against the oracles."""
+    from oracle import live_oracle, step_memory_oracle, step_time_oracle
+    from traceml_b200 import records as rec_mod
+    from traceml_b200 import replay
+    from traceml_b200.engine import Engine
+    from traceml_b200.live import StepCombinedComputer
+
+    S, W = 330, 256
+    recs = replay.make_step_replay(scenario, R, S, seed=77)
+    got = _summary(recs, W)
+    o = step_time_oracle.step_time_section(oracle_time_rows(recs, W), max_rows=W)
+    g = got["step_time"]
+    assert_struct(plain(g["data"]), plain({k: o["data"][k] for k in g["data"]}), "data")
+    assert_struct(plain(g["diagnosis"]), plain(o["diagnosis"]), "diagnosis")
+    steps = step_time_oracle.common_suffix_steps(o["data"]["aligned_step_metrics"], W)
+    ser = got["reduce"].time.series.cpu().numpy()
+    for mi, key in enumerate(step_time_oracle.METRIC_KEYS):
+        ref = step_time_oracle.metric_series(key, steps, o["data"]["aligned_step_metrics"])
+        np.testing.assert_allclose(ser[2 * mi], ref["median"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(ser[2 * mi + 1], ref["worst"], rtol=1e-12, atol=0)
+    mo = step_memory_oracle.step_memory_section(oracle_mem_rows(recs), window_size=W,
+                                                gpu_total_bytes=got["step_memory"]["gpu_total_bytes"])
+    assert_struct(plain(got["step_memory"]["per_global_rank"]), plain(mo["per_global_rank"]), "mem.rows")
+    assert_struct(strip_device(plain(got["step_memory"]["diagnosis"]))["primary"],
+                  strip_device(plain(mo["diagnosis"]))["primary"], "mem.primary")
+    # live tick on the same rings
+    engines = []
+    for r in range(R):
+        e = Engine(device=0, rank=r, world=R, ring_slots=512, proc_slots=64)
+        if len(recs[r]):
+            e.load_steps(recs[r])
+        engines.append(e)
+    torch.cuda.synchronize()
+    try:
+        tick = StepCombinedComputer(engines, window_size=100).compute_cli()
+    finally:
+        for e in engines:
+            e.close()
+    rows = {r: [rec_mod.step_record_to_wire(x, device=f"cuda:{r}") for x in recs[r]] for r in recs}
+    assert_struct(plain(tick), plain(live_oracle.live_step_time(rows, window=100)), "live", rel=REL_TOL)
