@@ -376,7 +376,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     R = max(1, args.gpus)
-    Ws = args.sample
+    Ws = max(2_000, args.sample // R)  # bounded: ~40 000 rows in all, a few seconds per step
     once = oracle_reduce_sample(R, Ws)
     for _ in range(max(1, min(args.warmup, 1))):
         once()
