@@ -60,3 +60,19 @@ def test_b_reduce_formula():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     assert bench.b_reduce(8, 10_000) == 8 * 10_000 * 64 + 128 * 10_000 + 72 * 8  # ~6.4 MB
+
+
+def test_summary_artifacts_are_written_atomically(tmp_path):
+    """final_summary.json / .txt: names and format of sdk/protocol.py:160-171, atomic replace."""
+    import json
+
+    from traceml_b200.summary import write_summary_artifacts
+
+    env = {"schema_version": "1.2", "step_time": {"x": 1.5}, "text": "Step Time: BALANCED"}
+    paths = write_summary_artifacts(env, str(tmp_path / "session"))
+    assert json.load(open(paths["json"])) == env
+    assert open(paths["json"]).read() == json.dumps(env, indent=2)
+    assert open(paths["txt"]).read() == "Step Time: BALANCED"
+    write_summary_artifacts(dict(env, text="again"), str(tmp_path / "session"))  # replace in place
+    assert open(paths["txt"]).read() == "again"
+    assert sorted(p.name for p in (tmp_path / "session").iterdir()) == ["final_summary.json", "final_summary.txt"]
