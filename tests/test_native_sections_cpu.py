@@ -89,3 +89,27 @@ def test_native_process_section_equals_python(g):
     assert_struct(plain(nat["process"]), plain(py["process"]), "process", rel=0.0)
     assert_struct(plain(nat["process"]["primary"]), g["process"]["diagnosis"]["primary"], "golden.primary")
     assert_struct(plain(nat["process"]["issues"]), g["process"]["diagnosis"]["issues"], "golden.issues")
+
+
+@pytest.mark.parametrize("pattern", [(0, 0, 1, 1), (0, 0, 0, 0, 0, 0), (0, 1, 0, 1, 0), (1, 0), (0, 1, 2, 0, 1, 2, 0)])
+def test_tie_breaks_with_identical_ranks(pattern):
+    """Ranks holding identical records: every per-rank value ties, so median / worst ranks are
+    decided purely by the tie-break rules (|delta|, value, rank / lowest rank wins) -- the
+    native rollups must make the same choices as sections.py."""
+    from traceml_b200 import replay
+
+    base = replay.make_step_replay("input_straggler", 3, 260, seed=5)
+    recs = {r: base[p].copy() for r, p in enumerate(pattern)}
+    pbase = replay.make_proc_replay("imbalance", 3, 120, seed=5)
+    procs = {r: pbase[p].copy() for r, p in enumerate(pattern)}
+    py, nat = both(recs, procs, 10_000)
+    for sec in ("step_time", "step_memory", "process"):
+        assert_struct(plain(nat[sec]), plain(py[sec]), sec, rel=0.0)
+    # and against the oracle (the reference's arithmetic) for the public rollup
+    from helpers import oracle_time_rows
+    from oracle import step_time_oracle
+
+    o = step_time_oracle.step_time_section(oracle_time_rows(recs, 10_000), max_rows=10_000)
+    for k in ("average", "median", "worst"):
+        assert_struct(plain(nat["step_time"]["global"][k]), plain(o["global"][k]), f"oracle.global.{k}", rel=0.0)
+    assert_struct(plain(nat["step_time"]["diagnosis"]), plain(o["diagnosis"]), "oracle.diagnosis", rel=0.0)
