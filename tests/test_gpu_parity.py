@@ -291,3 +291,39 @@ def test_more_than_eight_ranks(cuda, R, scenario):
             e.close()
     rows = {r: [rec_mod.step_record_to_wire(x, device=f"cuda:{r}") for x in recs[r]] for r in recs}
     assert_struct(plain(tick), plain(live_oracle.live_step_time(rows, window=100)), "live", rel=REL_TOL)
+
+
+def _fuzz_cases(n, seed):
+    import random
+
+    rng = random.Random(seed)
+    sc = ["balanced", "input_straggler", "compute_straggler", "straggler", "input_bound", "wait_heavy",
+          "compute_bound", "warmup", "ragged", "trend_worsening", "duplicates", "empty_rank", "no_overlap",
+          "mem_creep_confirmed", "mem_creep_early", "mem_imbalance", "mem_pressure"]
+    return [(rng.choice(sc), rng.choice([1, 2, 3, 4, 6, 8]), rng.choice([40, 90, 260, 520]),
+             rng.randrange(10_000), rng.choice([29, 128, 10_000]), rng.choice([None, None, 96]))
+            for _ in range(n)]
+
+
+@pytest.mark.parametrize("scenario,R,S,seed,W,slots", _fuzz_cases(24, 991))
+def test_random_scenarios_vs_oracle(cuda, scenario, R, S, seed, W, slots):
+    """Seeded random scenario / rank count / window / ring size through the kernels, against the
+    oracle: data, diagnosis, rollups, memory rows (ring smaller than the history included)."""
+    from oracle import step_memory_oracle, step_time_oracle
+    from traceml_b200 import replay
+
+    recs = replay.make_step_replay(scenario, R, S, seed)
+    got = _summary(recs, W, ring_slots=slots)
+    kept = {r: (recs[r][-slots:] if slots else recs[r]) for r in recs}
+    o = step_time_oracle.step_time_section(oracle_time_rows(kept, W), max_rows=W)
+    g = got["step_time"]
+    assert_struct(plain(g["data"]), plain({k: o["data"][k] for k in g["data"]}), "data")
+    assert_struct(plain(g["diagnosis"]), plain(o["diagnosis"]), "diagnosis")
+    for k in ("average", "median", "worst"):
+        assert_struct(plain(g["global"][k]), plain(o["global"][k]), f"global.{k}")
+    mo = step_memory_oracle.step_memory_section(oracle_mem_rows(kept), window_size=W,
+                                                gpu_total_bytes=got["step_memory"]["gpu_total_bytes"])
+    gd, od = strip_device(plain(got["step_memory"]["diagnosis"])), strip_device(plain(mo["diagnosis"]))
+    assert_struct(gd["primary"], od["primary"], "mem.primary")
+    assert_struct(gd["issues"], od["issues"], "mem.issues")
+    assert_struct(plain(got["step_memory"]["per_global_rank"]), plain(mo["per_global_rank"]), "mem.rows")
