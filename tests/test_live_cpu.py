@@ -211,3 +211,37 @@ def test_live_two_process_gloo(name):
     for r in range(world):
         assert_struct(plain(got[r]["cli"]), g["cli"], f"{name}.r{r}.cli", rel=0.0)
         assert_struct(plain(got[r]["dashboard"]), g["dashboard"], f"{name}.r{r}.dashboard", rel=0.0)
+
+
+def _live_fuzz(n, seed):
+    import random
+
+    rng = random.Random(seed)
+    sc = ["balanced", "input_straggler", "straggler", "wait_heavy", "ragged", "duplicates", "empty_rank",
+          "no_overlap", "warmup", "mem_imbalance", "mem_creep_confirmed", "trend_worsening"]
+    return [(rng.choice(sc), rng.choice([1, 2, 3, 5, 8]), rng.choice([30, 90, 260, 700, 2600]),
+             rng.randrange(10_000), rng.choice([7, 50, 100, 400])) for _ in range(n)]
+
+
+@pytest.mark.parametrize("scenario,R,S,seed,W", _live_fuzz(30, 515))
+def test_live_host_logic_random(scenario, R, S, seed, W):
+    """Seeded random cases: both live views over the engine double against their oracle."""
+    from fake_engine import FakeEngine
+    from helpers import assert_struct, plain
+    from oracle import live_oracle
+    from traceml_b200 import replay
+    from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
+
+    recs = replay.make_step_replay(scenario, R, S, seed)
+    engines = [FakeEngine(recs[r]) for r in sorted(recs)]
+    rows = wire_rows(recs)
+    t = StepCombinedComputer(engines, window_size=W, device=torch.device("cpu"))
+    assert_struct(plain(t._compute_impl(include_series=True, include_rank_heatmap=False)),
+                  plain(live_oracle.live_step_time(rows, window=W)), "time.cli", rel=0.0)
+    assert_struct(plain(t._compute_impl(include_series=False, include_rank_heatmap=True)),
+                  plain(live_oracle.live_step_time(rows, window=W, include_series=False,
+                                                   include_rank_heatmap=True)), "time.dash", rel=0.0)
+    m = StepMemoryCombinedComputer(engines, window_size=W, gpu_available=True, device=torch.device("cpu"))
+    assert_struct(plain(strip_dev(m._compute_impl())),
+                  plain(live_oracle.live_step_memory(mem_rows(recs), window=W, gpu_available=True)),
+                  "mem", rel=0.0)
