@@ -186,3 +186,52 @@ def test_live_memory_far_ahead_rank(cuda):
     ref = live_oracle.live_step_memory(rows, window=100, gpu_available=True)
     assert ref["metrics"][0]["coverage"]["ranks_present"] == 2
     assert_struct(plain(got), plain(ref), "far_ahead", rel=REL_TOL)
+
+
+def _live_fuzz(n, seed):
+    import random
+
+    rng = random.Random(seed)
+    sc = ["balanced", "input_straggler", "straggler", "wait_heavy", "ragged", "duplicates", "empty_rank",
+          "no_overlap", "warmup", "mem_imbalance", "mem_creep_confirmed", "trend_worsening"]
+    return [(rng.choice(sc), rng.choice([1, 2, 3, 5, 8]), rng.choice([30, 90, 260, 700, 2600]),
+             rng.randrange(10_000), rng.choice([7, 50, 100, 400]), rng.choice([None, 512]))
+            for _ in range(n)]
+
+
+@pytest.mark.parametrize("scenario,R,S,seed,W,slots", _live_fuzz(16, 616))
+def test_live_views_random_vs_oracle(cuda, scenario, R, S, seed, W, slots):
+    """Seeded random cases through the K7 kernels (ring wrap included) against the live oracle."""
+    from oracle import live_oracle
+    from traceml_b200 import records as rec_mod
+    from traceml_b200 import replay
+    from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
+
+    recs = replay.make_step_replay(scenario, R, S, seed)
+    engines = _engines(recs, ring_slots=slots)
+    try:
+        cli = StepCombinedComputer(engines, window_size=W).compute_cli()
+        t = StepCombinedComputer(engines, window_size=W)
+        with torch.cuda.stream(t._stream):
+            dash = t._compute_impl(include_series=False, include_rank_heatmap=True)
+        m = StepMemoryCombinedComputer(engines, window_size=W, gpu_available=True)
+        with torch.cuda.stream(m._stream):
+            mem = _strip_dev(m._compute_impl())
+    finally:
+        for e in engines:
+            e.close()
+    # the look-back never reaches past what the ring retains (minus the in-flight guard)
+    kept = {r: (recs[r][-(slots - 8):] if slots and len(recs[r]) > slots - 8 else recs[r]) for r in recs}
+    rows = {r: [rec_mod.step_record_to_wire(x, device=f"cuda:{r}") for x in kept[r]] for r in kept}
+    ref = live_oracle.live_step_time(rows, window=W)
+    if ref["metrics"]:
+        assert_struct(plain(cli), plain(ref), "cli", rel=REL_TOL)
+    else:  # compute_cli() wraps an empty tick with its stale message
+        assert cli["metrics"] == [] and cli["status_message"] == "No fresh step-combined data"
+    assert_struct(plain(dash), plain(live_oracle.live_step_time(rows, window=W, include_series=False,
+                                                                include_rank_heatmap=True)), "dash", rel=REL_TOL)
+    mrows = {r: [(int(s), float(a), float(v)) if (f & 1) else (int(s), None, None)
+                 for s, a, v, f in zip(kept[r]["step"], kept[r]["peak_alloc"], kept[r]["peak_resv"],
+                                       kept[r]["flags"])] for r in kept}
+    assert_struct(plain(mem), plain(live_oracle.live_step_memory(mrows, window=W, gpu_available=True)),
+                  "mem", rel=REL_TOL)
