@@ -31,9 +31,12 @@ def main():
 
     failures = 0
     for scenario, S, W in (("straggler", 700, 10_000), ("ragged", 900, 256), ("empty_rank", 300, 10_000),
-                           ("no_overlap", 120, 10_000), ("duplicates", 400, 100),
+                           ("no_overlap", 120, 10_000), ("duplicates", 400, 100), ("lagging", 700, 3),
                            ("input_straggler", 200_000, 150_000)):
-        recs_all = replay.make_step_replay(scenario, world, S, seed=11) if S <= 1000 else None
+        gen = "duplicates" if scenario == "lagging" else scenario
+        recs_all = replay.make_step_replay(gen, world, S, seed=11) if S <= 1000 else None
+        if scenario == "lagging":  # the last rank is far behind: the memory candidate limit (20 W) binds
+            recs_all[world - 1] = recs_all[world - 1][:150]
         mine = (recs_all[rank] if recs_all is not None else
                 replay.make_step_replay(scenario, world, S, seed=11, only_ranks=[rank])[rank])
         procs = replay.make_proc_replay("overhang", world, 500, seed=11, only_ranks=[rank])[rank]

@@ -327,3 +327,25 @@ def test_random_scenarios_vs_oracle(cuda, scenario, R, S, seed, W, slots):
     assert_struct(gd["primary"], od["primary"], "mem.primary")
     assert_struct(gd["issues"], od["issues"], "mem.issues")
     assert_struct(plain(got["step_memory"]["per_global_rank"]), plain(mo["per_global_rank"]), "mem.rows")
+
+
+@pytest.mark.parametrize("W,dup", [(1, False), (3, False), (3, True), (7, True)])
+def test_memory_candidate_limit_with_a_lagging_rank(cuda, W, dup):
+    """A tiny window over a long ring with one rank far behind: the reference only aligns the
+    newest max(20 W, W + 1) distinct steps of each rank (step_memory/loader.py:215), so the
+    memory section finds no common window while the time section (last W rows) is unaffected."""
+    from oracle import step_memory_oracle, step_time_oracle
+    from traceml_b200 import replay
+
+    recs = replay.make_step_replay("duplicates" if dup else "balanced", 3, 700, seed=123)
+    recs[1] = recs[1][:200]
+    got = _summary(recs, W)
+    o = step_time_oracle.step_time_section(oracle_time_rows(recs, W), max_rows=W)
+    assert_struct(plain(got["step_time"]["data"]), plain({k: o["data"][k] for k in got["step_time"]["data"]}), "data")
+    mo = step_memory_oracle.step_memory_section(oracle_mem_rows(recs), window_size=W,
+                                                gpu_total_bytes=got["step_memory"]["gpu_total_bytes"])
+    gd, od = strip_device(plain(got["step_memory"]["diagnosis"])), strip_device(plain(mo["diagnosis"]))
+    assert od["primary"]["reason"] == "No step-memory data yet."
+    assert_struct(gd["primary"], od["primary"], "mem.primary")
+    assert_struct(plain(got["step_memory"]["per_global_rank"]), plain(mo["per_global_rank"]), "mem.rows")
+    assert got["step_memory"]["window"]["n_steps"] == 0

@@ -479,6 +479,29 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
   tml_proc_agg pagg;
   memset(&pagg, 0, sizeof(pagg));
   if (args->proc_rows) CKT(tml_proc_reduce_collect(c, &pagg));
+  // Memory candidate limit (step_memory/loader.py:215): only the newest max(20 W, W + 1)
+  // distinct step ids of a rank enter the memory alignment.  The ring normally holds 1.5 W
+  // rows, so this binds only for a small window over a long ring; the rank then advertises
+  // the step id of its limit-th newest candidate as its lower bound, and every later stage
+  // works on [max lo, min hi] without ever seeing the older candidates.
+  {
+    const u64 limit = (u64)window * 20ull > (u64)window + 1ull ? (u64)window * 20ull : (u64)window + 1ull;
+    if (info.n_cand[TML_KIND_MEM] > limit) {
+      u64 thr;
+      if (info.dense[TML_KIND_MEM]) {
+        thr = info.hi[TML_KIND_MEM] - limit + 1;  // consecutive ids
+      } else {  // holes / re-flushed ids: select the newest `limit` of the rank's own candidates
+        const u64 lo = info.lo[TML_KIND_MEM], span = info.hi[TML_KIND_MEM] - lo + 1;
+        CKT(grow(&r.w->d_presence, &r.w->cap_presence, span));
+        CKT(tml_win_presence(c, TML_KIND_MEM, lo, span, r.w->d_presence, r.s));
+        tml_align_info own;
+        CKT(tml_win_select(c, TML_KIND_MEM, lo, span, r.w->d_presence, (uint32_t)limit, r.s, &own));
+        thr = own.start_step;
+      }
+      info.lo[TML_KIND_MEM] = thr;
+      info.n_cand[TML_KIND_MEM] = limit;
+    }
+  }
   const bool spec_handles = world > 1 && exchange != TML_XCHG_A2A;
   const int plen = args->proc_rows ? PROC_LEN : 0;
   const int slen = args->speculate ? ALIGN_LEN + (spec_handles ? HANDLE_LEN : 0) : 0;

@@ -302,6 +302,8 @@ class WindowReducer:
         if ev:
             k3a_ev = torch.cuda.Event(enable_timing=True)
             k3a_ev.record()
+        for l, e in enumerate(self.engines):
+            self._limit_memory_candidates(e, local_infos[l], window, stream)
         # Lock-step speculation: a rank whose own time window is dense assumes the common
         # window IS its window (true whenever the ranks run in lock step) and sends that
         # alignment -- sums and rows handle, nothing to launch -- with its bounds.  If the
@@ -405,6 +407,27 @@ class WindowReducer:
                                           if hasattr(e, "kernel_ms")))
         return ReduceOutput(window=window, ranks=ranks, infos=infos, time=t_res, mem=m_res,
                             exchange=mode, fused_pass=same, timings_ms=timings, proc_aggs=proc_aggs)
+
+    # ------------------------------------------------------------------ memory candidate limit
+    def _limit_memory_candidates(self, engine, info: Dict[str, Any], window: int, stream) -> None:
+        """Only the newest ``max(20 W, W + 1)`` distinct step ids of a rank enter the memory
+        alignment (step_memory/loader.py:215, oracle candidate_rows).  The ring normally holds
+        1.5 W rows, so this binds only for a small window over a long ring; then the rank
+        advertises the step id of its limit-th newest candidate as its lower bound -- every
+        later stage works on [max lo, min hi] and never sees the older candidates."""
+        limit = max(20 * window, window + 1)
+        if info["n_cand"][KIND_MEM] <= limit:
+            return
+        lo, hi = info["lo"][KIND_MEM], info["hi"][KIND_MEM]
+        if info["dense"][KIND_MEM]:  # consecutive ids
+            thr = hi - limit + 1
+        else:                        # holes / re-flushed ids: select the newest `limit` of its own
+            span = hi - lo + 1
+            own = torch.empty(span, dtype=torch.uint8, device=self.device)
+            engine.win_presence(KIND_MEM, lo, span, own, stream)
+            thr = int(engine.win_select(KIND_MEM, lo, span, own, limit, stream).start_step)
+        info["lo"][KIND_MEM] = int(thr)
+        info["n_cand"][KIND_MEM] = int(limit)
 
     # ------------------------------------------------------------------ native sequencing
     def _native_ok(self) -> bool:
