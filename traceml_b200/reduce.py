@@ -194,7 +194,9 @@ class ReduceOutput:
 class NativeReduceOutput:
     """What ``SummaryEngine.build`` returns as ``"reduce"`` on the native path: the cheap
     facts eagerly, the full ``ReduceOutput`` (per-rank windows, band sums, series view) only
-    if somebody asks -- the sections no longer need it."""
+    if somebody asks -- the sections no longer need it.  ``time.series`` / ``mem.series`` are
+    zero-copy views of the engine's own workspace: valid until the engine's next reduce or its
+    ``close()``; ``clone()`` them to keep them."""
 
     def __init__(self, reducer: "WindowReducer", o, window: int, proc_rows: Optional[int]):
         self.window = window
