@@ -205,9 +205,13 @@ def test_native_driver_equals_python_driver(cuda, scenario, S, W, slots):
             assert se.reducer._native_ok() == native
             out[native] = se.build(W, W)
             again = se.build(W, W)  # workspace reuse
-            again.pop("reduce")
+            red = again.pop("reduce")
             first = dict(out[native]); first.pop("reduce")
             assert_struct(plain(first), plain(again), "repeatable", rel=0.0)
+            # the series live in the engine's workspace: copy them out before it closes
+            series[native] = (red.time.series.clone() if red.time.n_common else None,
+                              red.mem.series.clone() if red.mem.n_common else None)
+            facts[native] = (red.exchange, red.fused_pass, red.time.n_common, red.mem.n_common)
         finally:
             e.close()
     a, b = out[True], out[False]
