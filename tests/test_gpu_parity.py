@@ -185,6 +185,8 @@ def test_large_window_properties(cuda):
     ("balanced", 300, 10_000, None), ("wait_heavy", 300, 128, None), ("duplicates", 240, 10_000, None),
     ("trend_worsening", 600, 10_000, None), ("mem_creep_confirmed", 300, 100, None),
     ("cpu_only", 120, 10_000, None), ("balanced", 1000, 200, 300), ("warmup", 40, 10_000, None),
+    # tiny window over a long ring: the memory candidate limit (20 W) binds -- dense and holey rings
+    ("balanced", 700, 3, None), ("duplicates", 700, 3, None), ("ragged", 900, 7, None),
 ])
 def test_native_driver_equals_python_driver(cuda, scenario, S, W, slots):
     """tml_reduce_run (csrc/tml_summary.cpp) against the Python staging of the same C-ABI
