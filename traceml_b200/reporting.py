@@ -198,5 +198,61 @@ def build_final_summary(res: Dict[str, Any], identities: Optional[Dict[int, Dict
     return env
 
 
-__all__ = ["build_final_summary", "reference_payloads", "reference_available", "default_identity",
+# ----------------------------------------------------------------------------- live views
+def to_reference_step_combined(result: Dict[str, Any]):
+    """``live.StepCombinedComputer`` result -> the reference's ``StepCombinedTimeResult``
+    (renderers/step_time/schema.py:12-88), what the kept CLI renderer / dashboard consume."""
+    from traceml.renderers.step_time.schema import (StepCombinedRankHeatmap, StepCombinedRankRow,
+                                                    StepCombinedTimeCoverage, StepCombinedTimeMetric,
+                                                    StepCombinedTimeResult, StepCombinedTimeSeries,
+                                                    StepCombinedTimeSummary)
+
+    metrics = [StepCombinedTimeMetric(
+        metric=m["metric"], clock=m["clock"],
+        series=StepCombinedTimeSeries(**m["series"]) if m["series"] else None,
+        summary=StepCombinedTimeSummary(**m["summary"]),
+        coverage=StepCombinedTimeCoverage(**m["coverage"])) for m in result["metrics"]]
+    heat = None
+    if result.get("rank_heatmap"):
+        h = result["rank_heatmap"]
+        heat = StepCombinedRankHeatmap(window_size=h["window_size"], steps_used=h["steps_used"],
+                                       metric_keys=list(h["metric_keys"]),
+                                       rows=[StepCombinedRankRow(rank=r["rank"], sums_ms=dict(r["sums_ms"]))
+                                             for r in h["rows"]],
+                                       sort_by=list(h["sort_by"]))
+    return StepCombinedTimeResult(metrics=metrics, status_message=result["status_message"], rank_heatmap=heat)
+
+
+def to_reference_step_memory_combined(result: Dict[str, Any]):
+    """``live.StepMemoryCombinedComputer`` result -> ``StepMemoryCombinedResult``
+    (renderers/step_memory/schema.py:8-72)."""
+    from traceml.renderers.step_memory.schema import (StepMemoryCombinedCoverage, StepMemoryCombinedMetric,
+                                                      StepMemoryCombinedResult, StepMemoryCombinedSeries,
+                                                      StepMemoryCombinedSummary)
+
+    metrics = [StepMemoryCombinedMetric(
+        metric=m["metric"], device=m.get("device"),
+        series=StepMemoryCombinedSeries(**m["series"]),
+        summary=StepMemoryCombinedSummary(**m["summary"]),
+        coverage=StepMemoryCombinedCoverage(**m["coverage"])) for m in result["metrics"]]
+    return StepMemoryCombinedResult(metrics=metrics, status_message=result["status_message"])
+
+
+class ReferenceComputerAdapter:
+    """Drop-in for the ``_computer`` attribute of the kept renderers
+    (renderers/step_time/renderer.py:56, step_memory/renderer.py:60): same ``compute_cli`` /
+    ``compute_dashboard`` methods, reference dataclasses out, this package's live computer in."""
+
+    def __init__(self, computer, convert):
+        self._computer, self._convert = computer, convert
+
+    def compute_cli(self):
+        return self._convert(self._computer.compute_cli())
+
+    def compute_dashboard(self):
+        return self._convert(self._computer.compute_dashboard())
+
+
+__all__ = ["to_reference_step_combined", "to_reference_step_memory_combined", "ReferenceComputerAdapter",
+           "build_final_summary", "reference_payloads", "reference_available", "default_identity",
            "to_reference_step_time", "to_reference_step_memory", "to_reference_process"]
