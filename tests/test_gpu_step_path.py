@@ -338,7 +338,7 @@ def test_final_summary_public_api(cuda):
             opt.step()
             opt.zero_grad(set_to_none=True)
     out = traceml.final_summary(print_text=False)
-    assert out is not None and out["schema_version"] == "1.2"
+    assert out is not None and out["schema_version"] == 1.2
     st = out["step_time"]
     if "data" in st:   # reference not installed on this box: native envelope
         assert st["data"]["training_steps"] == 65

@@ -81,3 +81,42 @@ def test_process_payload_via_kept_builder(g):
     payload = build_process_payload(data, diag)
     assert_struct(plain(payload), g["process"]["payload"], "payload", rel=1e-9)
     assert format_process_section_text(payload) == g["process"]["text"]
+
+
+@pytest.mark.parametrize("scenario,pscenario,R,S,W", [("input_straggler", "normal", 4, 460, 10_000),
+                                                      ("mem_imbalance", "overhang", 4, 260, 10_000),
+                                                      ("balanced", "high_cpu", 1, 300, 128)])
+def test_final_summary_envelope_equals_the_reference_report(tmp_path, scenario, pscenario, R, S, W):
+    """End to end: the reference's FinalReportGenerator over its SQLite vs build_final_summary
+    over this package's sections (engine double) -- same envelope keys, identical process /
+    step_time / step_memory payloads, identical printed summary apart from the System card
+    (the System section is outside this path)."""
+    import torch
+    from fake_engine import FakeEngine
+    from traceml.reporting.final import build_final_report_generator
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+
+    recs = replay.make_step_replay(scenario, R, S, seed=5)
+    procs = replay.make_proc_replay(pscenario, R, 200, seed=5)
+    db = str(tmp_path / "telemetry")
+    mg.build_db(db, step_records=recs, proc_records=procs)
+    ref = build_final_report_generator(summary_window_rows=W).generate(db)
+    se = sections.SummaryEngine([FakeEngine(recs[r], procs[r]) for r in range(R)],
+                                ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=R)
+    se.reducer.device = torch.device("cpu")
+    res = se.build(W, W)
+    ids = {r: {"global_rank": r, "local_rank": r, "node_rank": 0, "hostname": "b200-box",
+               "local_world_size": R, "world_size": R} for r in range(R)}
+    env = reporting.build_final_summary(res, ids)
+    assert set(ref) <= set(env) and env["schema_version"] == ref["schema_version"] == 1.2
+    for k in ("process", "step_time", "step_memory"):
+        assert_struct(plain(env[k]), plain(ref[k]), k, rel=1e-12)
+
+    def body(text):  # everything but the System card block
+        lines = text.splitlines()
+        i = next(n for n, l in enumerate(lines) if l.strip("| ").startswith("Process"))
+        return lines[:3] + lines[i:]
+
+    assert body(env["text"]) == body(ref["text"])

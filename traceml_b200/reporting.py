@@ -173,17 +173,28 @@ def reference_payloads(res: Dict[str, Any], identities: Dict[int, Dict[str, Any]
 
 def build_final_summary(res: Dict[str, Any], identities: Optional[Dict[int, Dict[str, Any]]] = None
                         ) -> Dict[str, Any]:
-    """final_summary envelope (reporting/final.py:254-267 key set)."""
+    """The final_summary envelope: key set and formats of reporting/final.py:254-267
+    (``schema_version 1.2, generated_at`` ISO-8601 UTC, ``duration_s, system, process,
+    step_time, step_memory, text``).  With the reference importable the kept builders produce
+    the section payloads and the kept ``final.py`` the combined text; the System section (NVML
+    sampler: out of this path's scope) stays empty."""
+    from datetime import datetime, timezone
+
     ranks = res["reduce"].ranks if "reduce" in res else []
     world = len(ranks) or 1
     identities = identities or {r: default_identity(r, world) for r in ranks}
-    env: Dict[str, Any] = {"schema_version": "1.2", "generated_at": time.time(),
-                           "engine": "traceml_b200"}
+    env: Dict[str, Any] = {"schema_version": 1.2, "generated_at": datetime.now(timezone.utc).isoformat(),
+                           "duration_s": None, "system": {}, "engine": "traceml_b200"}
     if reference_available():
+        from traceml.reporting import final as ref_final
+
         sec = reference_payloads(res, identities)
         for k in ("process", "step_time", "step_memory"):
-            env[k] = sec[k]["payload"]
-        env["text"] = "\n\n".join(sec[k]["text"] for k in ("process", "step_time", "step_memory"))
+            env[k] = dict(sec[k]["payload"])
+        env["duration_s"] = ref_final._summary_duration_s(env["step_time"], env["process"], env["system"])
+        env["text"] = ref_final._build_final_summary_text_from_sections(
+            system_summary=env["system"], process_summary=env["process"],
+            step_time_summary=env["step_time"], step_memory_summary=env["step_memory"])
     else:
         for k in ("process", "step_time", "step_memory"):
             env[k] = {kk: vv for kk, vv in res[k].items()} if isinstance(res[k], dict) else res[k]
