@@ -132,3 +132,39 @@ def test_wire_rows_from_records_match_reference_schema():
     m = step_record_to_memory_wire(r, device="cuda:3")
     assert set(m) == {"seq", "ts", "model_id", "device", "step", "peak_alloc", "peak_resv"}
     assert m["peak_alloc"] == float(int(r["peak_alloc"]))
+
+
+def test_kept_huggingface_integration_imports_against_this_package(monkeypatch):
+    """The kept ``integrations/huggingface.py`` with its single TraceML import line pointed at
+    this package: it must import (TRACEML_DISABLED: no engine needed), expose ``TraceMLTrainer``
+    on top of transformers' Trainer, and its bypass path must not touch the engine."""
+    import importlib.util
+    import os
+    import sys
+    import types
+
+    ref = "/root/reference/src/traceml/integrations/huggingface.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference not present on this box")
+    pytest.importorskip("transformers")
+    monkeypatch.setenv("TRACEML_DISABLED", "1")
+    from traceml_b200 import runtime
+
+    runtime.refresh_disabled()
+    try:
+        src = open(ref).read()
+        line = "from traceml.sdk.decorators_compat import trace_model_instance, trace_step"
+        assert src.count(line) == 1
+        src = src.replace(line, "from traceml_b200.sdk.decorators_compat import trace_model_instance, trace_step")
+        assert "traceml." not in src.replace("traceml_b200.", "")  # nothing else of TraceML is imported
+        mod = types.ModuleType("kept_hf_integration")
+        exec(compile(src, ref, "exec"), mod.__dict__)
+        from transformers import Trainer
+
+        assert issubclass(mod.TraceMLTrainer, Trainer) and mod.TRACEML_DISABLED is True
+        import traceml_b200.sdk.decorators_compat as compat
+
+        assert compat.trace_step is mod.trace_step
+    finally:
+        monkeypatch.delenv("TRACEML_DISABLED")
+        runtime.refresh_disabled()

@@ -127,6 +127,14 @@ def init(*, mode: str = "auto", patch_dataloader: Optional[bool] = None,
         return req
 
 
+def enable_legacy_decorator_auto_init() -> Optional[TraceMLInitConfig]:
+    """Importing the legacy decorator module used to install the automatic patches as a side
+    effect (sdk/initial.py:303-317); an explicit ``init()`` made earlier is respected."""
+    if is_initialized():
+        return get_init_config()
+    return init(mode="auto", _source="traceml.decorators")
+
+
 def start(**kwargs) -> TraceMLInitConfig:
     return init(**kwargs)
 
@@ -137,4 +145,4 @@ def _reset_for_tests() -> None:
         _CONFIG = None
 
 
-__all__ = ["TraceMLInitConfig", "init", "start", "get_init_config", "is_initialized"]
+__all__ = ["enable_legacy_decorator_auto_init", "TraceMLInitConfig", "init", "start", "get_init_config", "is_initialized"]
