@@ -168,3 +168,34 @@ def test_kept_huggingface_integration_imports_against_this_package(monkeypatch):
     finally:
         monkeypatch.delenv("TRACEML_DISABLED")
         runtime.refresh_disabled()
+
+
+def test_kept_lightning_callback_imports_against_this_package(monkeypatch):
+    """The kept ``integrations/lightning.py`` with its TraceML imports pointed at this package's
+    seam modules (same module paths, same names): it must import and define its callback.
+    (Lightning itself is stubbed: only ``Callback`` is needed at import time; the hook sequence
+    is exercised on the GPU by test_gpu_step_path.py::test_lightning_style_seam_sequence.)"""
+    import os
+    import sys
+    import types
+
+    ref = "/root/reference/src/traceml/integrations/lightning.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference not present on this box")
+    src = open(ref).read()
+    wanted = ["from traceml.runtime.state import", "from traceml.utils.flush_buffers import",
+              "from traceml.utils.step_memory import", "from traceml.utils.timing import"]
+    for w in wanted:
+        assert src.count(w) == 1, w
+    src = src.replace("from traceml.", "from traceml_b200.")
+    for name in ("lightning", "lightning.pytorch", "lightning.pytorch.callbacks"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    sys.modules["lightning.pytorch.callbacks"].Callback = type("Callback", (), {})
+    mod = types.ModuleType("kept_lightning_integration")
+    exec(compile(src, ref, "exec"), mod.__dict__)
+    cbs = [v for v in vars(mod).values() if isinstance(v, type) and v.__module__ == mod.__name__
+           and issubclass(v, sys.modules["lightning.pytorch.callbacks"].Callback)]
+    assert cbs, "the kept file defines its Lightning callback"
+    for name in ("get_trace_session_state", "flush_step_events", "StepMemoryTracker", "TimeEvent",
+                 "TimeScope", "record_event", "timed_region"):
+        assert getattr(mod, name).__module__.startswith("traceml_b200."), name
