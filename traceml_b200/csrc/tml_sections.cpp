@@ -151,9 +151,10 @@ bool layout_exists(unsigned long long n, unsigned long long min_points, double w
 }
 
 int run_diag(int (*fn)(const void*, char*, size_t), const void* in, S* out) {
-  std::vector<char> buf(1 << 16);
+  thread_local std::vector<char> buf;  // reused: no 64 KB zero-fill per rule engine per summary
+  if (buf.size() < (1u << 16)) buf.resize(1u << 16);
   int rc = fn(in, buf.data(), buf.size());
-  if (rc == TML_ERR_SMALL) { buf.resize(1 << 20); rc = fn(in, buf.data(), buf.size()); }
+  if (rc == TML_ERR_SMALL) { buf.resize(1u << 20); rc = fn(in, buf.data(), buf.size()); }
   if (rc != TML_OK) return rc;
   out->assign(buf.data());
   return TML_OK;
