@@ -4,15 +4,21 @@ Replaces, for the Step-Time / Step-Memory / Process sections, the reference's
 TCP -> SQLite -> single-core Python chain
 (``src/traceml/reporting/sections/*/loader.py`` + ``diagnostics/*``): every
 rank's window stays resident in its own HBM ring; ranks agree on the common
-step window with two tiny collectives, exchange their aligned 64-B rows once
-over NVLink (peer loads fused into the reduce kernel, or one NCCL all-gather),
-and each GPU reduces its shard of the steps.
+step window with one or two tiny collectives, exchange their aligned 64-B rows
+once over NVLink (peer loads fused into the reduce kernel, a step-sharded
+send/recv, or one NCCL all-gather), and each GPU reduces its shard of the steps.
 
-Host side only sequences kernels and collectives; all per-step arithmetic is
-in ``csrc/tml_engine.cu``, all rank-level rules in ``csrc/tml_diag.cpp``.
+Two drivers sequence the same C-ABI stages:
+  * production (one engine per process on a CUDA device): ``tml_reduce_run``
+    (``csrc/tml_summary.cpp``) runs stages and NCCL collectives natively on
+    torch.distributed's own communicator -- ``WindowReducer.run_native``;
+  * this module's Python staging: several engines per process ("local ranks":
+    how single-GPU tests play a whole job on one device), gloo on CPU, or when the
+    communicator cannot be borrowed.  It is also the executable specification of
+    the native driver; the two are held bit-identical by the tests.
 
-One process may drive several engines ("local ranks") -- production uses one,
-single-GPU tests use several to play a whole job on one device.
+All per-step arithmetic is in ``csrc/tml_engine.cu``, all rank-level rules in
+``csrc/tml_diag.cpp``.
 """
 
 from __future__ import annotations

@@ -6,7 +6,9 @@ The B200-native counterpart of
 reduce on the GPUs (``reduce.WindowReducer``), ``diagnose`` is the C++ rule
 engine (``csrc/tml_diag.cpp``).  The objects returned here are plain dicts with
 the reference's field names; ``reporting.py`` turns them into the reference's
-own dataclasses for the kept payload builders.
+own dataclasses for the kept payload builders.  With one engine per process the same
+objects come from ``tml_sections_json`` (``csrc/tml_sections.cpp``) in one JSON parse;
+this module is then the specification the native emitter is tested against.
 
 Also holds the O(R) public rollups the payload uses
 (``reporting/sections/step_time/model.py:77-105,284-498``,
