@@ -1366,6 +1366,17 @@ int tml_shutdown(tml_ctx* c) {
 
 // ---------------------------------------------------------------- step path
 
+// Entry points may be called from any host thread (a fresh thread's current device is 0): make the
+// context's device current before launching on one of its streams.  cudaGetDevice is a TLS read.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const tml_ctx* c) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != c->device) { prev = cur; cudaSetDevice(c->device); }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }  // the caller's current device is restored
+};
+
 static inline int check_capture(cudaStream_t s) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -1375,6 +1386,7 @@ static inline int check_capture(cudaStream_t s) {
 int tml_phase_begin(tml_ctx* c, uint32_t phase, void* stream) {
   if (!c || phase >= TML_MAX_PHASES) return TML_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);
   if (check_capture(s)) return TML_ERR_CAPTURE;
   u32 slot = c->next_slot;
   c->next_slot = (slot + 1u) % TML_N_SLOTS;
@@ -1388,6 +1400,7 @@ int tml_phase_begin(tml_ctx* c, uint32_t phase, void* stream) {
 int tml_phase_end(tml_ctx* c, uint32_t phase, int slot, void* stream) {
   if (!c || phase >= TML_MAX_PHASES || slot < 0 || slot >= (int)TML_N_SLOTS) return TML_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);
   if (check_capture(s)) return TML_ERR_CAPTURE;
   k_stamp_end<<<1, 32, 0, s>>>(c->d_state, (u32)slot, phase, (u32)(c->commits % TML_N_EPOCHS));
   c->launches += 1;
@@ -1414,6 +1427,7 @@ int tml_step_commit(tml_ctx* c, uint64_t step, uint64_t peak_alloc, uint64_t pea
                     uint32_t flags, double host_ts, void* stream) {
   if (!c) return TML_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);
   if (check_capture(s)) return TML_ERR_CAPTURE;
   CommitArgs a;
   a.step = step; a.host_ts = host_ts;
@@ -1491,6 +1505,7 @@ int tml_proc_commit(tml_ctx* c, const tml_proc_record* sample, void* stream) {
   if (!c || !sample) return TML_ERR_ARG;
   std::lock_guard<std::mutex> g(c->proc_mu);
   cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);  // the sampler thread is not the training thread
   k_proc_commit<<<1, 32, 0, s>>>(c->d_state, c->d_pring, c->proc_slots, c->d_pmirror,
                                   c->pmirror_slots, c->d_page, *sample);
   c->launches += 1;

@@ -62,6 +62,16 @@ std::atomic<bool> g_sampler_run{false};
 std::atomic<uint64_t> g_sampler_seq{0};
 std::atomic<uint64_t> g_sampler_late{0};
 
+// Last line of defence (the package registers an atexit that unbinds first): a joinable
+// std::thread destroyed at static destruction is std::terminate, which would mask the run's
+// real exit code.  Declared after g_sampler, so it is destroyed before it.
+struct SamplerJoin {
+  ~SamplerJoin() {
+    if (g_sampler_run.exchange(false) && g_sampler.joinable()) g_sampler.join();
+    else if (g_sampler.joinable()) g_sampler.join();
+  }
+} g_sampler_join;
+
 void bind(const std::string& lib_path, uint64_t ctx, int64_t device) {
   void* h = dlopen(lib_path.c_str(), RTLD_NOW | RTLD_GLOBAL);
   if (!h) throw std::runtime_error(std::string("dlopen failed: ") + dlerror());

@@ -57,6 +57,12 @@ class Engine:
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
+            # the step glue / native sampler hold this context's raw pointer: unbind them first
+            import sys
+
+            timing = sys.modules.get("traceml_b200.utils.timing")
+            if timing is not None and getattr(timing, "_ENG", None) is self:
+                timing._reset()
             self._lib.tml_shutdown(self._h)
             self._h = C.c_void_p()
 

@@ -37,6 +37,7 @@ class _Flags(threading.local):
     r_fwd = None
     r_bwd = None
     r_h2d = None
+    h2d_depth = 0
 
 
 _TLS = _Flags()
@@ -134,11 +135,20 @@ def _tensor_to(self, *args, **kwargs):
     t = _TLS
     if not t.h2d or not should_time_h2d(self, args, kwargs):
         return _ORIG_TENSOR_TO(self, *args, **kwargs)
+    if t.h2d_depth > 0:
+        # a .to() issued inside a timed .to() (tensor subclasses, batch wrappers): the shared
+        # region object is open -- time the inner call with its own object
+        with timed_region(H2D, "step", True):
+            return _ORIG_TENSOR_TO(self, *args, **kwargs)
     region = t.r_h2d
     if region is None:
         region = t.r_h2d = timed_region(H2D, "step", True)
-    with region:
-        return _ORIG_TENSOR_TO(self, *args, **kwargs)
+    t.h2d_depth += 1
+    try:
+        with region:
+            return _ORIG_TENSOR_TO(self, *args, **kwargs)
+    finally:
+        t.h2d_depth -= 1
 
 
 def patch_h2d() -> None:

@@ -85,6 +85,11 @@ def get_engine(device: Optional[int] = None):
         # reference retention: 1.5 x window rows per rank (reporting/config.py:13-35)
         slots = int(os.environ.get("TRACEML_RING_SLOTS", str(int(window * 1.5))))
         if _ENGINE is not None:
+            import sys as _sys
+
+            timing = _sys.modules.get("traceml_b200.utils.timing")
+            if timing is not None:
+                timing._reset()  # unbind the fast path + join the sampler before the context goes
             _ENGINE.close()
         _ENGINE = Engine(device=dev, rank=rank, world=world, ring_slots=max(1, slots),
                          proc_slots=max(1, slots))
@@ -92,7 +97,16 @@ def get_engine(device: Optional[int] = None):
         return _ENGINE
 
 
+def peek_engine():
+    """The process engine if the training thread has created it, else None.  Side threads
+    (sampler, render tick) use this: only the training thread -- whose current CUDA device is
+    the rank's device -- may create the engine."""
+    return _ENGINE
+
+
 def shutdown_engine() -> None:
+    """Join the native sampler, unbind the step glue, then free the context -- in that order:
+    the sampler thread and the bound fast path hold raw pointers into the context."""
     global _ENGINE, _ENGINE_DEVICE
     with _LOCK:
         import sys
@@ -104,6 +118,13 @@ def shutdown_engine() -> None:
             _ENGINE.close()
         _ENGINE = None
         _ENGINE_DEVICE = None
+
+
+import atexit as _atexit
+
+# a run that raises, or never calls TraceMLRuntime.stop(), must still join the native sampler
+# before static destruction (a joinable std::thread at exit is std::terminate)
+_atexit.register(shutdown_engine)
 
 
 class TraceMLRuntime:
@@ -154,10 +175,19 @@ class TraceMLRuntime:
     def _tick(self) -> None:
         from ..samplers import drain_to_wire
 
-        eng = get_engine()
+        # never create the engine here: a new host thread's current device is 0, so an engine
+        # created from the sampler thread would land on cuda:0 for every rank
+        eng = peek_engine()
+        if eng is None:
+            return
         if self._proc is not None:
-            self._proc.sample(eng)
-        out = drain_to_wire(eng)
+            if not self._proc._cuda_safe():
+                return  # distributed job before init_process_group (process_sampler.py:150-158)
+            import torch
+
+            with torch.cuda.device(eng.device):
+                self._proc.sample(eng)
+        out = drain_to_wire(eng, ram_total=getattr(self._proc, "ram_total", None))
         self.steps_seen += len(out["step_time"])
         self.dropped += out["dropped"]
         self.ticks += 1
@@ -191,5 +221,5 @@ class TraceMLRuntime:
             print(f"[TraceML] final tick failed: {exc}", file=sys.stderr)
 
 
-__all__ = ["TraceMLRuntime", "TraceSessionState", "get_engine", "shutdown_engine", "disabled", "refresh_disabled",
+__all__ = ["TraceMLRuntime", "TraceSessionState", "get_engine", "peek_engine", "shutdown_engine", "disabled", "refresh_disabled",
            "get_trace_session_state", "reset_trace_session_state", "summary_window_rows"]

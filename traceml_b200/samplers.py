@@ -17,17 +17,47 @@ from .records import (PROC_FLAG_GPU_AVAILABLE, PROC_FLAG_HAS_GPU_METRICS, proc_r
                       step_record_to_memory_wire, step_record_to_wire)
 
 
-def drain_to_wire(engine, device: Optional[str] = None) -> Dict[str, Any]:
+_HOST_CONSTS: Dict[str, Any] = {}
+
+
+def host_constants() -> Dict[str, Any]:
+    """Per-host constants of a process wire row (samplers/process_sampler.py:96-123):
+    ``ram_total`` = psutil.virtual_memory().total, ``gpu_count`` = torch.cuda.device_count().
+    Read once; they are not in the 64-B device record."""
+    if not _HOST_CONSTS:
+        try:
+            import psutil
+
+            _HOST_CONSTS["ram_total"] = float(psutil.virtual_memory().total)
+        except Exception:
+            _HOST_CONSTS["ram_total"] = float(os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES"))
+        try:
+            import torch
+
+            _HOST_CONSTS["gpu_count"] = int(torch.cuda.device_count()) if torch.cuda.is_available() else 0
+        except Exception:
+            _HOST_CONSTS["gpu_count"] = 0
+    return _HOST_CONSTS
+
+
+def drain_to_wire(engine, device: Optional[str] = None, ram_total: Optional[float] = None,
+                  gpu_count: Optional[int] = None) -> Dict[str, Any]:
     """Completed records since the last call as wire rows
     (samplers/schema/step_time_schema.py:85-96, step_memory.py:41-58, process.py:139-150)."""
     dev = device or f"cuda:{engine.device}"
     recs, dropped = engine.drain()
     procs, pdropped = engine.proc_drain()
     now = time.time()
+    if procs is not None and len(procs) and (ram_total is None or gpu_count is None):
+        hc = host_constants()
+        ram_total = hc["ram_total"] if ram_total is None else ram_total
+        gpu_count = hc["gpu_count"] if gpu_count is None else gpu_count
     return {
         "step_time": [step_record_to_wire(r, device=dev) for r in recs],
         "step_memory": [step_record_to_memory_wire(r, device=dev, ts=now) for r in recs],
-        "process": [proc_record_to_wire(p, pid=os.getpid(), device_index=engine.device) for p in procs],
+        "process": [proc_record_to_wire(p, pid=os.getpid(), device_index=engine.device,
+                                        ram_total=float(ram_total or 0.0), gpu_count=int(gpu_count or 0))
+                    for p in procs],
         "dropped": int(dropped) + int(pdropped),
     }
 

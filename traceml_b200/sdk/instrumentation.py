@@ -79,6 +79,8 @@ class trace_step:
             try:
                 _timing._resolve()
                 fast = _timing._FAST
+            except _timing._Quiet:
+                pass  # reported once by _resolve
             except Exception as exc:
                 _log("engine start failed", exc)
         if fast is not None:

@@ -42,12 +42,63 @@ def write_summary_artifacts(summary: Dict[str, Any], session_root: str) -> Dict[
     return paths
 
 
+_CALLS = 0
+MAX_RANKS = 64  # TML_MAX_RANKS (include/traceml_b200.h): ranks one reduce can align
+
+
+def _rendezvous(timeout_sec: float, poll_interval_sec: float) -> bool:
+    """All ranks have entered ``final_summary`` -- or nobody proceeds.
+
+    The reference's call is a file RPC that any rank may issue alone and that returns ``None``
+    after ``timeout_sec`` (``sdk/summary_client.py:35-110``).  Here the summary is a collective,
+    so the time-out is honoured in front of it: ranks count themselves in through the process
+    group's store and poll every ``poll_interval_sec``; the first rank to see everyone present
+    publishes "go", the first to run out of time publishes "abort" (compare-and-set, so the
+    decision is unanimous) and every rank returns ``None`` -- fail open, nothing hangs.
+    """
+    import time
+
+    import torch.distributed as dist
+
+    global _CALLS
+    _CALLS += 1
+    try:
+        store = dist.distributed_c10d._get_default_store()
+    except Exception:
+        return True  # no store to meet on: enter the collective directly
+    world = dist.get_world_size()
+    key_n, key_d = f"traceml_b200/final_summary/{_CALLS}/n", f"traceml_b200/final_summary/{_CALLS}/d"
+    deadline = time.monotonic() + max(0.0, float(timeout_sec))
+    try:
+        store.add(key_n, 1)
+        while True:
+            if store.add(key_n, 0) >= world:
+                return store.compare_set(key_d, "", "go") == b"go"
+            try:
+                decided = store.compare_set(key_d, "", "")  # read without deciding
+            except Exception:
+                decided = b""
+            if decided in (b"go", b"abort"):
+                return decided == b"go"
+            if time.monotonic() >= deadline:
+                return store.compare_set(key_d, "", "abort") == b"go"
+            time.sleep(max(1e-3, float(poll_interval_sec)))
+    except Exception as exc:
+        import sys
+
+        print(f"[TraceML] final_summary rendezvous failed ({exc}); entering the reduce directly", file=sys.stderr)
+        return True
+
+
 def final_summary(*, timeout_sec: float = 30.0, poll_interval_sec: float = 0.1,
                   print_text: bool = False, rank0_only: bool = True,
                   window_rows: Optional[int] = None,
                   session_root: Optional[str] = None) -> Optional[Dict[str, Any]]:
-    """Collective over the default process group when one is initialised.  ``session_root``
-    (default: ``$TRACEML_SESSION_ROOT`` if set): where rank 0 also writes the artifacts."""
+    """Collective over the default process group when one is initialised; ``timeout_sec`` /
+    ``poll_interval_sec`` bound the wait for the other ranks (``None`` is returned on every rank
+    if one never arrives -- same fail-open contract as ``sdk/summary_client.py:35``).
+    ``session_root`` (default: ``$TRACEML_SESSION_ROOT`` if set): where rank 0 also writes the
+    artifacts."""
     if disabled():
         return None
     import torch
@@ -57,10 +108,21 @@ def final_summary(*, timeout_sec: float = 30.0, poll_interval_sec: float = 0.1,
     from .reporting import build_final_summary
     from .sections import SummaryEngine
 
+    import sys
+
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed and dist.get_world_size() > MAX_RANKS:
+        if dist.get_rank() == 0:
+            print(f"[TraceML] final_summary: {dist.get_world_size()} ranks exceed the {MAX_RANKS} one "
+                  "reduce aligns; no summary produced", file=sys.stderr)
+        return None
+    if distributed and not _rendezvous(timeout_sec, poll_interval_sec):
+        print(f"[TraceML] final_summary: not every rank arrived within {timeout_sec:.1f} s; "
+              "no summary produced", file=sys.stderr)
+        return None
     eng = get_engine()
     torch.cuda.current_stream(torch.device("cuda", eng.device)).synchronize()
-    comm = TorchDistComm() if (dist.is_available() and dist.is_initialized()
-                               and dist.get_world_size() > 1) else LocalComm()
+    comm = TorchDistComm() if distributed else LocalComm()
     res = SummaryEngine([eng], comm).build(window_rows or summary_window_rows(),
                                            window_rows or summary_window_rows())
     if rank0_only and comm.index != 0:

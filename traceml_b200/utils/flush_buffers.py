@@ -17,9 +17,9 @@ from .step_memory import take_pending
 def flush_step_events(model, step: int) -> None:
     if disabled():
         return
-    try:
-        from . import timing
+    from . import timing
 
+    try:
         eng = timing._ENG or timing._resolve()
         pend = take_pending(model)
         alloc = resv = 0
@@ -31,6 +31,8 @@ def flush_step_events(model, step: int) -> None:
         if rc < 0:
             eng.step_discard()
             print(f"[TraceML] step {step} not committed (status {rc})", file=sys.stderr)
+    except timing._Quiet:
+        pass  # engine resolution failed and was reported once
     except Exception as exc:
         print(f"[TraceML] flush failed: {exc}", file=sys.stderr)
 

@@ -35,10 +35,21 @@ _ENG = None         # the process engine, resolved on first use
 _FAST = None        # traceml_b200._tml_step bound to that engine (None: ctypes path)
 
 
+_RESOLVE_FAILED: Optional[str] = None  # a failed engine resolution is cached and printed once
+
+
 def _resolve():
     """First region of the process: create the engine, bind the native step glue."""
-    global _ENG, _FAST
-    eng = get_engine()
+    global _ENG, _FAST, _RESOLVE_FAILED
+    if _RESOLVE_FAILED is not None:
+        raise _Quiet(_RESOLVE_FAILED)
+    try:
+        eng = get_engine()
+    except Exception as exc:
+        _RESOLVE_FAILED = f"{type(exc).__name__}: {exc}"
+        print(f"[TraceML] telemetry engine unavailable, regions are not recorded: {_RESOLVE_FAILED}",
+              file=sys.stderr)
+        raise _Quiet(_RESOLVE_FAILED) from exc
     if _raw_stream is None:
         _bind_torch()
     fast = None
@@ -53,8 +64,13 @@ def _resolve():
     return eng
 
 
+class _Quiet(RuntimeError):
+    """Engine resolution already failed and was reported: callers stay silent."""
+
+
 def _reset() -> None:
-    global _ENG, _FAST
+    global _ENG, _FAST, _RESOLVE_FAILED
+    _RESOLVE_FAILED = None
     if _FAST is not None:
         try:
             _FAST.unbind()
@@ -127,18 +143,23 @@ class timed_region:
     """Context manager timing one region.  Class-based (not a generator) so the
     per-region host cost is two C calls plus a handful of attribute writes."""
 
-    __slots__ = ("phase", "gpu", "record", "slot", "t0", "eng")
+    __slots__ = ("phase", "gpu", "record", "slot", "t0", "eng", "on")
 
     def __init__(self, name: str, scope: Any = TimeScope.STEP, use_gpu: bool = True):
         self.phase = phase_of(name)
         self.gpu = bool(use_gpu)
         sc = scope.value if isinstance(scope, TimeScope) else str(scope)
-        self.record = (sc == "step") and not disabled()
+        self.on = (sc == "step") and not disabled()  # static: does this region record at all
+        self.record = self.on                        # per use: cleared when one setup fails
         self.slot = -1
         self.t0 = 0
         self.eng = None
 
     def __enter__(self):
+        # region objects are reused (instrumentation/patches.py): one failed setup must not
+        # silence the phase for the rest of the process
+        self.record = self.on
+        self.slot = -1
         if not self.record:
             return self
         try:
@@ -153,6 +174,8 @@ class timed_region:
                     self.t0 = _perf_ns()  # graph capture / launch failure: host clock
             else:
                 self.t0 = _perf_ns()
+        except _Quiet:
+            self.record = False
         except Exception as exc:  # timing setup failed: user code still runs
             self.record = False
             print(f"[TraceML] timed_region setup failed: {exc}", file=sys.stderr)
@@ -190,6 +213,8 @@ def record_event(evt: TimeEvent) -> None:
         ms = evt.gpu_time_ms if evt.gpu_time_ms is not None else (evt.cpu_end - evt.cpu_start) * 1000.0
         eng = _ENG or _resolve()
         eng._host(eng._h, phase_of(evt.name), max(0, int(round(float(ms) * 1.0e6))))
+    except _Quiet:
+        pass
     except Exception as exc:
         print(f"[TraceML] record_event failed: {exc}", file=sys.stderr)
 
