@@ -296,7 +296,7 @@ def step_overhead(device, world, local, quick=False):
         import torch.distributed as dist
         from oracle import live_oracle
         from traceml_b200 import records as rec_mod
-        from traceml_b200 import replay
+        import replay
         from traceml_b200.engine import Engine
         from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
         from traceml_b200.reduce import LocalComm, TorchDistComm
@@ -345,7 +345,7 @@ def oracle_reduce_sample(R: int, W: int, seed: int = 1):
     """Time the oracle (port of the reference's CPU reduce) on R ranks x W rows."""
     from helpers import oracle_mem_rows, oracle_proc_rows, oracle_time_rows
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
-    from traceml_b200 import replay
+    import replay
 
     recs = replay.make_step_replay("balanced", R, W, seed)
     procs = replay.make_proc_replay("normal", R, 2000, seed)
@@ -427,7 +427,8 @@ def main():
     rank, local, world = dist_setup()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    from traceml_b200 import replay, sections
+    import replay
+    from traceml_b200 import sections
     from traceml_b200.engine import Engine
     from traceml_b200.reduce import LocalComm, TorchDistComm
 

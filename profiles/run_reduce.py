@@ -5,9 +5,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
-from traceml_b200 import replay, sections  # noqa: E402
+import replay  # noqa: E402
+from traceml_b200 import sections  # noqa: E402
 from traceml_b200.engine import Engine  # noqa: E402
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000

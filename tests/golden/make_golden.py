@@ -31,13 +31,14 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, "/root/reference/src")
 
 import numpy as np  # noqa: E402
 
 from oracle import process_oracle, step_memory_oracle, step_time_oracle  # noqa: E402
 from traceml_b200 import records as rec_mod  # noqa: E402
-from traceml_b200 import replay  # noqa: E402
+import replay  # noqa: E402
 
 from traceml.aggregator.sqlite_writers import process as ref_proc_w  # noqa: E402
 from traceml.aggregator.sqlite_writers import step_memory as ref_mem_w  # noqa: E402

@@ -27,7 +27,7 @@ import make_golden as mg  # noqa: E402  (puts ROOT and the reference on sys.path
 
 from oracle import live_oracle  # noqa: E402
 from traceml_b200 import records as rec_mod  # noqa: E402
-from traceml_b200 import replay  # noqa: E402
+import replay  # noqa: E402
 
 from traceml.renderers.step_memory.common import (  # noqa: E402
     StepMemoryMetricsDB, build_step_memory_combined_result)

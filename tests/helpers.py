@@ -9,7 +9,7 @@ from typing import Any, Dict
 import numpy as np
 
 from traceml_b200 import records as rec_mod
-from traceml_b200 import replay
+import replay
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

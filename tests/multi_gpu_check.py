@@ -25,7 +25,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from helpers import assert_struct, oracle_mem_rows, oracle_proc_rows, oracle_time_rows, plain, strip_device
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
-    from traceml_b200 import replay, sections
+    import replay
+    from traceml_b200 import sections
     from traceml_b200.engine import Engine
     from traceml_b200.reduce import TorchDistComm
 

@@ -17,7 +17,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .records import (
+from traceml_b200.records import (
     FLAG_HAS_MEM,
     PHASE_BACKWARD,
     PHASE_DATALOADER,

@@ -105,7 +105,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 def test_replay_digest_is_stable():
-    from traceml_b200 import replay
+    import replay
 
     a = replay.make_step_replay("ragged", 3, 50, seed=8)
     b = replay.make_step_replay("ragged", 3, 50, seed=8)

@@ -13,7 +13,7 @@ pytest.importorskip("traceml.reporting.sections.step_time", reason="reference no
 
 from helpers import assert_struct, load_golden, plain, proc_replay_for, step_replay_for  # noqa: E402
 from traceml_b200 import records as rec_mod  # noqa: E402
-from traceml_b200 import replay  # noqa: E402
+import replay  # noqa: E402
 from traceml_b200.compat import SQLiteCompatWriter  # noqa: E402
 
 

@@ -19,7 +19,8 @@ def _worker(rank, world, scenario, S, W, init_file, out_dir, exchange, dense=Fal
     sys.path.insert(0, os.path.dirname(HERE))
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     from fake_engine import FakeEngine
-    from traceml_b200 import replay, sections
+    import replay
+    from traceml_b200 import sections
     from traceml_b200.reduce import TorchDistComm
 
     recs = replay.make_step_replay(scenario, world, S, seed=3)
@@ -47,7 +48,7 @@ def test_two_rank_reduce_matches_oracle(scenario, S, W, exchange):
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
     from helpers import (assert_struct, oracle_mem_rows, oracle_proc_rows, oracle_time_rows, plain,
                          strip_device)
-    from traceml_b200 import replay
+    import replay
 
     world = 2
     with tempfile.TemporaryDirectory() as td:

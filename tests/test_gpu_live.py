@@ -42,7 +42,7 @@ def _engines(records, ring_slots=None):
 
 @pytest.mark.parametrize("name", CASES)
 def test_live_vs_reference_golden(cuda, name):
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer
 
     g = json.load(open(os.path.join(LIVE, name + ".json")))
@@ -74,7 +74,7 @@ def test_live_ring_wrap_and_oracle(cuda):
     """The ring wrapped many times; the tick must see only the newest look-back rows."""
     from oracle import live_oracle
     from traceml_b200 import records as rec_mod
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer
 
     R, S, W = 4, 3000, 100
@@ -141,7 +141,7 @@ def _strip_dev(res):
 
 @pytest.mark.parametrize("name", MEM_CASES)
 def test_live_memory_vs_reference_golden(cuda, name):
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepMemoryCombinedComputer
 
     g = json.load(open(os.path.join(LIVE, name + ".json")))
@@ -168,7 +168,7 @@ def test_live_memory_far_ahead_rank(cuda):
     """A rank thousands of steps ahead of the slowest: its in-range rows lie beyond the first
     look-back and the ring has wrapped; the tick widens locally and stays exact."""
     from oracle import live_oracle
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepMemoryMetricsComputer
 
     recs = replay.make_step_replay("balanced", 2, 6000, 3)
@@ -204,7 +204,7 @@ def test_live_views_random_vs_oracle(cuda, scenario, R, S, seed, W, slots):
     """Seeded random cases through the K7 kernels (ring wrap included) against the live oracle."""
     from oracle import live_oracle
     from traceml_b200 import records as rec_mod
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
 
     recs = replay.make_step_replay(scenario, R, S, seed)

@@ -28,7 +28,8 @@ def cuda():
 
 
 def _summary(records, window, procs=None, ring_slots=None, ranks=None):
-    from traceml_b200 import replay, sections
+    import replay
+    from traceml_b200 import sections
     from traceml_b200.engine import Engine
 
     R = len(records) if records is not None else len(procs)
@@ -85,7 +86,7 @@ def test_step_memory_vs_golden(cuda, g):
 @pytest.mark.parametrize("g", [g for g in STEP if "step_memory_with_total" in g],
                          ids=[g["case"] for g in STEP if "step_memory_with_total" in g])
 def test_step_memory_pressure_vs_golden(cuda, g):
-    from traceml_b200 import replay
+    import replay
 
     recs = step_replay_for(g)
     procs = replay.make_proc_replay("normal", g["ranks"], 50, g["seed"])
@@ -115,7 +116,7 @@ def test_process_vs_golden(cuda, g):
 def test_series_vs_oracle(cuda):
     """Per-step cross-rank median / worst series, element by element."""
     from oracle import step_memory_oracle, step_time_oracle
-    from traceml_b200 import replay
+    import replay
 
     R, S, W = 5, 777, 512
     recs = replay.make_step_replay("ragged", R, S, seed=42)
@@ -140,7 +141,7 @@ def test_ring_wrap_and_window(cuda):
     """Ring smaller than the history: only the retained rows count
     (the reference prunes to 1.5 x window rows, sqlite_writer.py:394-424)."""
     from oracle import step_time_oracle
-    from traceml_b200 import replay
+    import replay
 
     R, S, slots, W = 3, 1000, 300, 200
     recs = replay.make_step_replay("balanced", R, S, seed=5)
@@ -156,7 +157,8 @@ def test_large_window_properties(cuda):
     """BASELINE-size window (W = 10^6, R = 8): size-independent properties --
     identical ranks => median == worst == the rank's own series; permuting the
     ranks leaves every series bit-identical."""
-    from traceml_b200 import _abi, replay, sections
+    import replay
+    from traceml_b200 import _abi, sections
     from traceml_b200.engine import Engine
     from traceml_b200.reduce import WindowReducer
 
@@ -191,7 +193,8 @@ def test_large_window_properties(cuda):
 def test_native_driver_equals_python_driver(cuda, scenario, S, W, slots):
     """tml_reduce_run (csrc/tml_summary.cpp) against the Python staging of the same C-ABI
     stages, one rank: every section identical, bit for bit."""
-    from traceml_b200 import replay, sections
+    import replay
+    from traceml_b200 import sections
     from traceml_b200.engine import Engine
 
     recs = replay.make_step_replay(scenario, 1, S, seed=31)[0]
@@ -230,7 +233,8 @@ def test_native_driver_equals_python_driver(cuda, scenario, S, W, slots):
 def test_native_driver_vs_reference_golden(cuda, name):
     """The native driver against the reference's own outputs (one-rank goldens)."""
     from helpers import load_golden
-    from traceml_b200 import replay, sections
+    import replay
+    from traceml_b200 import sections
     from traceml_b200.engine import Engine
 
     g = load_golden(name)
@@ -259,7 +263,7 @@ def test_more_than_eight_ranks(cuda, R, scenario):
     tick, numpy's blocked pairwise order for the per-step sums: both against the oracles."""
     from oracle import live_oracle, step_memory_oracle, step_time_oracle
     from traceml_b200 import records as rec_mod
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.engine import Engine
     from traceml_b200.live import StepCombinedComputer
 
@@ -315,7 +319,7 @@ def test_random_scenarios_vs_oracle(cuda, scenario, R, S, seed, W, slots):
     """Seeded random scenario / rank count / window / ring size through the kernels, against the
     oracle: data, diagnosis, rollups, memory rows (ring smaller than the history included)."""
     from oracle import step_memory_oracle, step_time_oracle
-    from traceml_b200 import replay
+    import replay
 
     recs = replay.make_step_replay(scenario, R, S, seed)
     got = _summary(recs, W, ring_slots=slots)
@@ -340,7 +344,7 @@ def test_memory_candidate_limit_with_a_lagging_rank(cuda, W, dup):
     newest max(20 W, W + 1) distinct steps of each rank (step_memory/loader.py:215), so the
     memory section finds no common window while the time section (last W rows) is unaffected."""
     from oracle import step_memory_oracle, step_time_oracle
-    from traceml_b200 import replay
+    import replay
 
     recs = replay.make_step_replay("duplicates" if dup else "balanced", 3, 700, seed=123)
     recs[1] = recs[1][:200]

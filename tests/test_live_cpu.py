@@ -48,7 +48,7 @@ def wire_rows(records):
 def test_live_oracle_matches_reference_golden(name):
     from helpers import assert_struct, plain
     from oracle import live_oracle
-    from traceml_b200 import replay
+    import replay
 
     g = load(name)
     recs = replay.make_step_replay(g["scenario"], g["ranks"], g["steps"], g["seed"])
@@ -67,7 +67,7 @@ def test_live_host_logic_with_engine_double(name):
     intersection, assembly) must reproduce the reference's result exactly."""
     from fake_engine import FakeEngine
     from helpers import assert_struct, plain
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer
 
     g = load(name)
@@ -87,7 +87,7 @@ def test_live_memory_oracle_and_host_logic(name):
     from fake_engine import FakeEngine
     from helpers import assert_struct, plain
     from oracle import live_oracle
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepMemoryCombinedComputer
 
     g = load(name)
@@ -107,7 +107,7 @@ def test_live_memory_far_ahead_rank_widens_lookback():
     from fake_engine import FakeEngine
     from helpers import assert_struct, plain
     from oracle import live_oracle
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepMemoryCombinedComputer
 
     recs = replay.make_step_replay("balanced", 2, 6000, 3)
@@ -123,7 +123,7 @@ def test_live_memory_far_ahead_rank_widens_lookback():
 def test_live_stale_handling():
     """compute.py:103-123, 424-446: an empty tick serves the last good result."""
     from fake_engine import FakeEngine
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer
 
     recs = replay.make_step_replay("balanced", 2, 60, 1)
@@ -149,7 +149,7 @@ def _worker(rank, world, name, init_file, out_dir):
     sys.path.insert(0, os.path.dirname(HERE))
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     from fake_engine import FakeEngine
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer
     from traceml_b200.reduce import TorchDistComm
 
@@ -170,7 +170,7 @@ def _mem_worker(rank, world, name, init_file, out_dir):
     sys.path.insert(0, os.path.dirname(HERE))
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     from fake_engine import FakeEngine
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepMemoryCombinedComputer
     from traceml_b200.reduce import TorchDistComm
 
@@ -229,7 +229,7 @@ def test_live_host_logic_random(scenario, R, S, seed, W):
     from fake_engine import FakeEngine
     from helpers import assert_struct, plain
     from oracle import live_oracle
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer, StepMemoryCombinedComputer
 
     recs = replay.make_step_replay(scenario, R, S, seed)

@@ -36,7 +36,7 @@ def test_kept_renderers_render_identically(scenario, R, S, seed):
     from fake_engine import FakeEngine
     from traceml.renderers.step_memory.renderer import StepMemoryRenderer
     from traceml.renderers.step_time.renderer import StepCombinedRenderer
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.live import StepCombinedComputer, StepMemoryMetricsComputer
     from traceml_b200.reporting import (ReferenceComputerAdapter, to_reference_step_combined,
                                         to_reference_step_memory_combined)

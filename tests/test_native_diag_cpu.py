@@ -131,7 +131,7 @@ def _agg_from_records(recs, max_rows):
 
 @pytest.mark.parametrize("g", PROC, ids=[g["case"] for g in PROC])
 def test_process_rules_native(g):
-    from traceml_b200 import replay
+    import replay
 
     procs = proc_replay_for(g)
     aggs = {r: sections.proc_agg_dict(_agg_from_records(procs[r], g["max_rows"]),

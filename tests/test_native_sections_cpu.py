@@ -54,7 +54,8 @@ def fill_run_out(red, window, proc_rows):
 
 def both(records, procs, window):
     from fake_engine import FakeEngine
-    from traceml_b200 import _abi, replay, sections
+    import replay
+    from traceml_b200 import _abi, sections
 
     R = len(records) if records is not None else len(procs)
     empty = replay.make_step_replay("balanced", 1, 0, 0)[0]
@@ -96,7 +97,7 @@ def test_tie_breaks_with_identical_ranks(pattern):
     """Ranks holding identical records: every per-rank value ties, so median / worst ranks are
     decided purely by the tie-break rules (|delta|, value, rank / lowest rank wins) -- the
     native rollups must make the same choices as sections.py."""
-    from traceml_b200 import replay
+    import replay
 
     base = replay.make_step_replay("input_straggler", 3, 260, seed=5)
     recs = {r: base[p].copy() for r, p in enumerate(pattern)}

@@ -20,7 +20,8 @@ if not reporting.reference_available():
 
 from oracle import step_memory_oracle, step_time_oracle  # noqa: E402
 from test_native_diag_cpu import _agg_from_records  # noqa: E402
-from traceml_b200 import replay, sections  # noqa: E402
+import replay  # noqa: E402
+from traceml_b200 import sections  # noqa: E402
 
 STEP = golden_cases("step")
 PROC = golden_cases("process")

@@ -25,7 +25,8 @@ def _cases(n, seed):
 def test_sections_vs_oracle_random(scenario, pscenario, R, S, seed, W):
     from fake_engine import FakeEngine
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
-    from traceml_b200 import _abi, replay, sections
+    import replay
+    from traceml_b200 import _abi, sections
     from test_native_sections_cpu import fill_run_out
 
     recs = replay.make_step_replay(scenario, R, S, seed)

@@ -20,7 +20,7 @@ class _Engine:
 
 
 def test_samplers_publish_reference_tables_once():
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.samplers import (ProcessSampler, RecordTap, StepMemorySampler, StepTimeSampler,
                                        TableStore)
 

@@ -120,7 +120,7 @@ def test_forward_targets_include_ddp_and_fsdp_inner():
 
 
 def test_wire_rows_from_records_match_reference_schema():
-    from traceml_b200 import replay
+    import replay
     from traceml_b200.records import step_record_to_memory_wire, step_record_to_wire
 
     r = replay.make_step_replay("balanced", 1, 3, seed=0)[0][1]

@@ -12,7 +12,7 @@ The public surface mirrors ``src/traceml/api.py:11-135`` of the reference::
         with traceml.trace_step(model):
             ...
 
-Submodules that only describe data (``records``, ``replay``) import without
+Submodules that only describe data (``records``) import without
 the CUDA extension; everything that records or reduces telemetry loads
 ``libtraceml_b200.so`` and raises if it is missing -- there is no CPU fallback.
 """
