@@ -819,8 +819,13 @@ def diagnosis_result(metrics, th, per_rank_timing=None):
 
 def diagnose_summary(rank_signals, *, max_rows, per_rank_step_metrics=None,
                      thresholds=None, min_steps_for_diag=SUMMARY_MIN_STEPS_FOR_DIAG,
-                     return_metrics=False):
-    """adapters.py:232-355 (build_summary_step_diagnosis_result)."""
+                     return_metrics=False, precomputed=None):
+    """adapters.py:232-355 (build_summary_step_diagnosis_result).
+
+    ``precomputed`` (oracle/fast_oracle.py, large windows): ``{"steps_used", "completed_step",
+    "series": {metric_key: {"steps", "median", "worst"}}}`` -- the per-step series already
+    reduced with numpy instead of the per-step Python loop of ``metric_series``; everything
+    downstream is this function unchanged."""
     th = dict(thresholds or SUMMARY_THRESHOLDS)
     if not rank_signals:
         return None
@@ -830,14 +835,19 @@ def diagnose_summary(rank_signals, *, max_rows, per_rank_step_metrics=None,
     if min_steps < int(min_steps_for_diag):
         return warmup_result(int(min_steps), int(min_steps_for_diag), int(max_steps))
     common, series = [], {}
-    if per_rank_step_metrics:
+    if precomputed is not None:
+        series = dict(precomputed["series"])
+    elif per_rank_step_metrics:
         common = common_suffix_steps(per_rank_step_metrics, max_rows=max_rows)
         for mk in METRIC_KEYS:
             series[mk] = metric_series(mk, common, per_rank_step_metrics)
+    n_common = int(precomputed["steps_used"]) if precomputed is not None else len(common)
+    last_common = (int(precomputed["completed_step"]) if precomputed is not None
+                   else (int(common[-1]) if common else 0))
     coverage = {
         "expected_steps": int(max_rows),
-        "steps_used": int(len(common)) if common else int(min_steps),
-        "completed_step": int(common[-1]) if common else 0,
+        "steps_used": n_common if n_common else int(min_steps),
+        "completed_step": last_common if n_common else 0,
         "world_size": len(ranks), "ranks_present": len(ranks),
         "incomplete": False,
     }
