@@ -4,7 +4,7 @@
 BASELINE.json metric: "per-step profiling overhead (us) at 1/2/4/8 ranks;
 cross-rank reduce GB/s".  One invocation measures both legs:
 
-  reduce leg   (``metric``/``value``/``roofline``/``e2e``)
+  reduce leg   (``metric``/``value``/``roofline``/``e2e``/``parity``/``default_window``)
       workload = BASELINE config 4's NVLink-reduce stress replay: every rank holds
       W step records (default W = 4e6 ~ 1 kHz x 67 min) plus 60 000 process samples.
       A "step" is one full cross-rank window reduce (align -> exchange -> per-step
@@ -12,14 +12,23 @@ cross-rank reduce GB/s".  One invocation measures both legs:
       value = algorithmic bytes B_reduce(R, W) = R*W*64 + 128*W + 72*R per step / time,
       records resident in HBM.  e2e = same, but each step starts from HOST (pinned)
       StepRecord buffers: H2D of W*128 B per rank + reduce + results back on the host.
+      parity = the W-sized result checked against the numpy oracle (oracle/fast_oracle.py,
+      pinned == to the row-level oracle, pinned == to the unmodified reference) on the same
+      seed, outside the timed region.  default_window = the reference's default W = 10^4 on
+      the same seed in BOTH arms: this engine's time next to the UNMODIFIED reference's
+      (baseline/_ref, separate process), and their summaries compared field by field.
   step leg     (``step_overhead``)
       BASELINE config 2: synthetic ResNet-18 (batch 64x3x224x224, DDP when N > 1)
       and the isolated tiny-MLP micro-harness; per-step wall of untraced vs traced
-      (this engine, auto mode) vs the reference's timer path (oracle port).
+      (this engine, auto mode); the reference's real ``traceml.trace_step`` is timed by
+      baseline/reference_legs.py in its own process (rank 0).
 
-``--impl reference`` runs the reference's own CPU algorithm (the oracle port --
-the reference is pure Python and cannot travel to the GPU box) on a bounded
-sample of the same workload, rank 0 only.
+``--impl reference`` runs the UNMODIFIED reference (``baseline/_ref``: ``pip install --target``
+of /root/reference, git-ignored, travels with the snapshot) in a separate process that maps none
+of this repository's native code: its own SQLite projection writers + its three summary
+sections on a bounded sample of the same workload (K timed steps, W warm-up), the default-window
+line at full size, and the real ``traceml.trace_step`` overhead leg.  If ``baseline/_ref`` is
+missing it falls back to the oracle port and says so (``cpu_baseline.kind: "port"``).
 
 Launch: ``python bench.py --gpus N --steps K --warmup W`` (N = 1) or under
 ``python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...``.
@@ -149,12 +158,11 @@ def resnet18(num_classes=10):
 
 
 def step_overhead(device, world, local, quick=False):
-    """Per-step wall: untraced vs this engine (auto mode) vs the reference timer path."""
+    """Per-step wall: untraced vs this engine (auto mode).  The reference's real
+    ``traceml.trace_step`` runs in its own process (baseline/reference_legs.py, rank 0)."""
     import traceml_b200 as traceml
-    from oracle.timer_oracle import ReferenceTimerPath  # cpu_baseline leg only
 
     traceml.init(mode="auto")
-    ref = ReferenceTimerPath()
     out = {}
 
     def run_arm(arm, model, opt, xs, ys, n):
@@ -166,35 +174,18 @@ def step_overhead(device, world, local, quick=False):
             if arm == "untraced":
                 xd, yd = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
                 loss = lossf(model(xd), yd); loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
-            elif arm == "b200":
+            else:
                 with traceml.trace_step(model):
                     xd, yd = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
                     loss = lossf(model(xd), yd); loss.backward(); opt.step(); opt.zero_grad(set_to_none=True)
-            else:  # reference timer path (oracle port), phases wrapped by hand
-                with ref.trace_step(model):
-                    with ref.timed_region("_traceml_internal:h2d_time"):
-                        xd = x.to(device, non_blocking=True)
-                    with ref.timed_region("_traceml_internal:h2d_time"):
-                        yd = y.to(device, non_blocking=True)
-                    with ref.timed_region("_traceml_internal:forward_time"):
-                        loss = lossf(model(xd), yd)
-                    with ref.timed_region("_traceml_internal:backward_time"):
-                        loss.backward()
-                    with ref.timed_region("_traceml_internal:optimizer_step"):
-                        opt.step()
-                    opt.zero_grad(set_to_none=True)
-                if i % 64 == 63:
-                    ref.sample()  # the sampler thread's work, amortised
         torch.cuda.synchronize(device)
-        if arm == "reference":
-            ref.sample()
         return (time.perf_counter() - t0) / n * 1.0e6
 
     def harness(name, model, xs, ys, n, cycles):
         opt = torch.optim.SGD(model.parameters(), lr=1e-3)
-        for arm in ("untraced", "b200", "reference"):
+        for arm in ("untraced", "b200"):
             run_arm(arm, model, opt, xs, ys, max(5, n // 4))  # warm-up
-        res = {"untraced": [], "b200": [], "reference": []}
+        res = {"untraced": [], "b200": []}
         for _ in range(cycles):
             for arm in res:
                 res[arm].append(run_arm(arm, model, opt, xs, ys, n))
@@ -202,9 +193,7 @@ def step_overhead(device, world, local, quick=False):
         out[name] = {
             "untraced_us": base,
             "b200_us": statistics.median(res["b200"]),
-            "reference_us": statistics.median(res["reference"]),
             "b200_overhead_us": statistics.median(res["b200"]) - base,
-            "reference_overhead_us": statistics.median(res["reference"]) - base,
             "steps_per_cycle": n, "cycles": cycles,
         }
 
@@ -341,11 +330,37 @@ def step_overhead(device, world, local, quick=False):
 
 
 # ----------------------------------------------------------------------------- reference arm
+REF_LEGS = os.path.join(ROOT, "baseline", "reference_legs.py")
+DEFAULT_W = 10_000          # the reference's default summary window (reporting/config.py:13)
+DEFAULT_PROC_ROWS = 2_000
+
+
+def ref_available() -> bool:
+    return os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "traceml"))
+
+
+def ref_leg(argv, timeout=1500) -> dict:
+    """Run baseline/reference_legs.py (the UNMODIFIED reference from baseline/_ref) in its own
+    process -- no module of this repository's engine is imported there -- and parse its JSON."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_ADDR",
+                        "MASTER_PORT", "TORCHELASTIC_RUN_ID", "PYTHONPATH")}
+    try:
+        p = subprocess.run([sys.executable, REF_LEGS] + [str(a) for a in argv], capture_output=True,
+                           text=True, timeout=timeout, env=env, cwd=ROOT)
+        lines = [ln for ln in p.stdout.strip().splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not lines:
+            return {"error": f"rc={p.returncode}: {(p.stderr or p.stdout)[-400:]}"}
+        return json.loads(lines[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
 def oracle_reduce_sample(R: int, W: int, seed: int = 1):
-    """Time the oracle (port of the reference's CPU reduce) on R ranks x W rows."""
+    """Fallback only (no baseline/_ref): the oracle port of the reference's CPU reduce."""
+    import replay
     from helpers import oracle_mem_rows, oracle_proc_rows, oracle_time_rows
     from oracle import process_oracle, step_memory_oracle, step_time_oracle
-    import replay
 
     recs = replay.make_step_replay("balanced", R, W, seed)
     procs = replay.make_proc_replay("normal", R, 2000, seed)
@@ -362,8 +377,8 @@ def oracle_reduce_sample(R: int, W: int, seed: int = 1):
 
 
 def workload_config(R: int, W: int) -> dict:
-    """The `config` both arms report: the workload is the same, the reference arm times a
-    bounded sample of it."""
+    """The `config` both arms report, key for key: the workload is the same; the reference arm
+    times a bounded sample of it (described under ``cpu_baseline.sample``, not here)."""
     return {"workload": f"BASELINE config 4 reduce-stress replay: R={R} ranks x W={W} step "
                         "records/rank (128 B) + 60000 process samples/rank; full window "
                         "reduce + diagnosis per step",
@@ -372,50 +387,289 @@ def workload_config(R: int, W: int) -> dict:
             "algorithmic_bytes_per_step": b_reduce(R, W)}
 
 
+def summary_digest(sections: dict) -> dict:
+    """The comparable core of a summary, same shape from either arm: status per section and the
+    public rollups ``global.{median,worst}`` = {metric: {value, idx}} (a15 / a16)."""
+    out = {}
+    for name in ("step_time", "step_memory", "process"):
+        sec = sections.get(name) or {}
+        g = sec.get("global") or {}
+        out[name] = {"status": sec.get("status"),
+                     "median": {k: v for k, v in (g.get("median") or {}).items()},
+                     "worst": {k: v for k, v in (g.get("worst") or {}).items()}}
+    return out
+
+
+def compare_digests(mine: dict, ref: dict, rel: float = 1e-9) -> dict:
+    """status and idx exact, values within ``rel`` (SURVEY 8d tolerances)."""
+    bad, checked = [], 0
+    for name in ("step_time", "step_memory", "process"):
+        a, b = mine.get(name) or {}, ref.get(name) or {}
+        if a.get("status") != b.get("status"):
+            bad.append(f"{name}.status {a.get('status')!r} != {b.get('status')!r}")
+        checked += 1
+        for roll in ("median", "worst"):
+            for metric, rv in (b.get(roll) or {}).items():
+                mv = (a.get(roll) or {}).get(metric)
+                if mv is None:
+                    if name != "process":  # process rollups are compared where both sides emit them
+                        bad.append(f"{name}.{roll}.{metric} missing")
+                    continue
+                checked += 1
+                if str(mv.get("idx")) != str(rv.get("idx")):
+                    bad.append(f"{name}.{roll}.{metric}.idx {mv.get('idx')} != {rv.get('idx')}")
+                x, y = mv.get("value"), rv.get("value")
+                if (x is None) != (y is None) or (x is not None and abs(float(x) - float(y)) > rel * max(abs(float(y)), 1e-300)):
+                    bad.append(f"{name}.{roll}.{metric}.value {x!r} !~ {y!r}")
+    return {"ok": not bad, "fields_checked": checked, "mismatches": bad[:8]}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     R = max(1, args.gpus)
-    Ws = max(2_000, args.sample // R)  # bounded: ~40 000 rows in all, a few seconds per step
-    once = oracle_reduce_sample(R, Ws)
-    for _ in range(max(1, min(args.warmup, 1))):
-        once()
-    times = [once() for _ in range(max(1, min(args.steps, 5)))]
-    t = statistics.median(times)
-    val = b_reduce(R, Ws) / t / 1e9
+    W = int(args.window)
+    K, Wm = max(1, args.steps), max(0, args.warmup)
+    Ws = max(500, args.sample // R)  # bounded: ~40 000 rows in all, a few seconds per step
     line = {
-        "impl": "reference", "metric": "cross_rank_reduce_GBps", "value": val, "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": dict(workload_config(R, int(args.window)),
-                       sample=f"each step = R={R} ranks x {Ws} rows of that workload through the oracle port "
-                              "of the reference's Python reduce (rows already parsed: no SQLite/JSON)"),
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": "port",
-                         "sample": f"R={R} x W={Ws} rows, median of {len(times)}; {t / (R * Ws) * 1e6:.1f} us/row"},
-        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "host_cores": os.cpu_count(),
+        "impl": "reference", "metric": "cross_rank_reduce_GBps", "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": K, "warmup": Wm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(R, W), "host_cores": os.cpu_count(),
     }
-    if torch.cuda.is_available() and not args.no_overhead:
-        try:
-            line["step_overhead"] = step_overhead(torch.device("cuda", 0), 1, 0, quick=True)
-        except Exception as exc:
-            line["step_overhead"] = {"error": str(exc)}
+    if ref_available():
+        red = ref_leg(["--leg", "reduce", "--ranks", R, "--rows", Ws, "--steps", K, "--warmup", Wm,
+                       "--proc-rows", DEFAULT_PROC_ROWS])
+        if "error" in red:
+            print(json.dumps({"impl": "reference", "unavailable": red["error"][:300]}))
+            return
+        t = sum(red["s_per_step"]) / len(red["s_per_step"])
+        val = b_reduce(R, Ws) / t / 1e9
+        line.update({
+            "value": val, "ms_per_step": t * 1e3,
+            "cpu_baseline": {
+                "value": val, "unit": "GB/s", "cores": 1, "kind": "reference",
+                "sample": f"each step = the UNMODIFIED reference (baseline/_ref, own process): "
+                          f"StepTime/StepMemory/Process SummarySection.build(db) on R={R} ranks x {Ws} rows of the "
+                          f"workload, SQLite written by the reference's own projection writers; "
+                          f"{red['us_per_row']:.1f} us/row, single-threaded Python (1 of {os.cpu_count()} cores)",
+                "sections_s": red["s_sections_median"], "sqlite_projection": red["sqlite_projection"]},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_version": red.get("reference_version"),
+        })
+        # the reference's own default window, full size, same seed as the product arm's leg
+        dw = ref_leg(["--leg", "reduce", "--ranks", R, "--rows", DEFAULT_W, "--window", DEFAULT_W,
+                      "--steps", 1, "--warmup", 0, "--proc-rows", DEFAULT_PROC_ROWS])
+        if "error" not in dw:
+            line["default_window"] = {
+                "window": DEFAULT_W, "ranks": R, "ms": dw["s_per_step_median"] * 1e3,
+                "GBps": b_reduce(R, DEFAULT_W) / dw["s_per_step_median"] / 1e9,
+                "summary": summary_digest(dw["summary"]), "same_config_as_product_arm": True}
+        else:
+            line["default_window"] = dw
+        if torch.cuda.is_available() and not args.no_overhead:
+            line["step_overhead"] = ref_leg(["--leg", "overhead", "--quick"])
+    else:
+        once = oracle_reduce_sample(R, Ws)
+        for _ in range(Wm):
+            once()
+        times = [once() for _ in range(K)]
+        t = sum(times) / len(times)
+        val = b_reduce(R, Ws) / t / 1e9
+        line.update({
+            "value": val, "ms_per_step": t * 1e3,
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": "port",
+                             "sample": f"baseline/_ref missing: oracle port, R={R} x W={Ws} rows pre-parsed"},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- parity (outside timing)
+def _gather(obj, world):
+    if world <= 1:
+        return [obj]
+    out = [None] * world
+    torch.distributed.all_gather_object(out, obj)
+    return out
+
+
+def parity_check(recs, res, W, rank, world, device, ram_total):
+    """The W-sized result of THIS run against the numpy oracle on the same seed.
+
+    Every rank restates its own window with numpy (reference-order sums, exact integer memory
+    sums); rank 0 assembles the sections through the pinned row-level oracle's own rule code.
+    Series: every step at N = 1; at N > 1 a strided sample plus the last 10 000 steps (all the
+    trend rules read) of every rank's shard -- the rows are gathered, not regenerated."""
+    from helpers import assert_struct, plain, strip_device
+    from oracle import fast_oracle as fo
+
+    t0 = time.perf_counter()
+    part = fo.rank_part(recs, W)
+    mem = fo.mem_part(recs, W)
+    red = res["reduce"]
+    n = int(red.time.n_common)
+    steps = part["steps"] if part else np.zeros(0, np.int64)
+    bounds = _gather((int(steps[0]) if steps.size else None, int(steps[-1]) if steps.size else None,
+                      int(steps.size)), world)
+    lock_step = all(b == bounds[0] for b in bounds) and bounds[0][2] > 0 and \
+        bounds[0][1] - bounds[0][0] + 1 == bounds[0][2] and n == bounds[0][2]
+    if not lock_step:
+        return {"checked": False, "why": "ranks not in lock step: the numpy oracle's gathered-sample mode covers "
+                                         "the bench replay only"}
+    common = steps
+    al = fo.aligned_part(part, common)
+    # sampled steps: everything at N = 1, else stride + tail
+    if world == 1:
+        idx = np.arange(n)
+    else:
+        stride = max(1, n // 200_000)
+        idx = np.unique(np.concatenate([np.arange(0, n, stride), np.arange(max(0, n - fo.TAIL), n)]))
+    ser = red.time.series  # [16, n] device view, this rank's shard valid
+    lo, hi = red.time.shard if getattr(red.time, "shard", None) else (0, n)
+    mine = idx[(idx >= lo) & (idx < hi)]
+    dev_vals = ser[:, torch.from_numpy(mine).to(device)].cpu().numpy() if mine.size else np.zeros((16, 0))
+    payload = {
+        "summary": part["summary"], "n": part["n"], "aligned": al["summary"],
+        "rows": al["rows"][idx], "series_idx": mine, "series_vals": dev_vals,
+        "mem_sum": (int(mem["alloc"].sum(dtype=np.uint64)), int(mem["resv"].sum(dtype=np.uint64))) if mem else None,
+        "mem_peak": (int(mem["alloc"].max()), int(mem["resv"].max())) if mem else None,
+        "latest": int(recs["step"].max()),
+    }
+    allp = _gather(payload, world)
+    if rank != 0:
+        return None
+    R = world
+    ser_ref = fo.series16(np.stack([p["rows"] for p in allp]))          # [16, len(idx)]
+    got = np.full((16, idx.size), np.nan)
+    pos = {int(v): k for k, v in enumerate(idx.tolist())}
+    for p in allp:
+        cols = [pos[int(v)] for v in p["series_idx"].tolist()]
+        got[:, cols] = p["series_vals"]
+    series_equal = bool(np.array_equal(got, ser_ref))
+    n_bad = int((got != ser_ref).sum())
+    tail = min(fo.TAIL, n)
+    tail_cols = [pos[v] for v in range(n - tail, n)]
+    parts = {r: {"summary": allp[r]["summary"]} for r in range(R)}
+    aligned = {r: {"summary": allp[r]["aligned"]} for r in range(R)}
+    ref_t = fo.step_time_from_parts(parts, aligned, n, int(common[0]), int(common[-1]), W,
+                                    ser_ref[:, tail_cols], common[n - tail:], max(p["latest"] for p in allp))
+    bad = []
+
+    def chk(a, b, what, rel=1e-9):
+        try:
+            assert_struct(plain(a), plain(b), what, rel)
+        except AssertionError as exc:
+            bad.append(str(exc)[:200])
+
+    gt = res["step_time"]
+    chk(gt["data"]["aligned_window"], ref_t["data"]["aligned_window"], "time.window")
+    chk(gt["data"]["aligned_summary"], ref_t["data"]["aligned_summary"], "time.aligned_summary")
+    chk(gt["data"]["per_global_rank_summary"], ref_t["data"]["per_global_rank_summary"], "time.per_rank_summary")
+    chk(gt["diagnosis"], ref_t["diagnosis"], "time.diagnosis")
+    chk(gt["global"], ref_t["global"], "time.global")
+    chk(gt["overview"], ref_t["overview"], "time.overview")
+    sums_bit_exact = all(plain(gt["data"]["aligned_summary"]).get(str(r)) == plain(ref_t["data"]["aligned_summary"]).get(str(r))
+                         for r in range(R))
+    # step memory: means from exact integer sums, peaks, series columns 12..15
+    from oracle import step_memory_oracle as smo
+
+    gm = res["step_memory"]
+    means = {str(r): {"peak_allocated_bytes": float(allp[r]["mem_sum"][0]) / n,
+                      "peak_reserved_bytes": float(allp[r]["mem_sum"][1]) / n} for r in range(R)
+             if allp[r]["mem_sum"] is not None}
+    chk(gm["per_global_rank"], means, "mem.per_rank_means")
+    chk(gm["global"], smo.rollup_points(means), "mem.global")
+    metrics = []
+    for i, name in enumerate(("peak_allocated", "peak_reserved")):
+        peaks = [float(allp[r]["mem_peak"][i]) for r in range(R)]
+        med_peak, worst_peak = float(smo.median2(peaks)), float(max(peaks))
+        metrics.append({"metric": name,
+                        "series": {"steps": [int(s) for s in common[n - tail:]],
+                                   "median": ser_ref[12 + 2 * i, tail_cols].tolist(),
+                                   "worst": ser_ref[13 + 2 * i, tail_cols].tolist()},
+                        "summary": {"window_size": W, "steps_used": n, "median_peak": med_peak, "worst_peak": worst_peak,
+                                    "worst_rank": int(peaks.index(worst_peak)),
+                                    "skew_ratio": float(worst_peak / med_peak if med_peak > 0 else 0.0),
+                                    "skew_pct": float((worst_peak - med_peak) / med_peak if med_peak > 0 else 0.0)},
+                        "coverage": {"expected_steps": W, "steps_used": n, "completed_step": int(common[-1]),
+                                     "world_size": R, "ranks_present": R, "incomplete": False}})
+    ref_md = strip_device(smo.diagnose_summary(metrics, gm.get("gpu_total_bytes")))
+    gd = strip_device(plain(gm["diagnosis"]))
+    chk(gd["primary"], ref_md["primary"], "mem.diagnosis.primary")
+    chk(gd["issues"], ref_md["issues"], "mem.diagnosis.issues")
+    return {
+        "checked": True, "ok": (not bad) and series_equal, "window": W, "ranks": R,
+        "oracle": "oracle/fast_oracle.py (numpy; pinned == row-level oracle == unmodified reference)",
+        "labels": {"step_time": (ref_t["diagnosis"] or {}).get("primary", {}).get("status"),
+                   "step_memory": ref_md["primary"]["status"]},
+        "idx": {"median_total_step": ref_t["global"]["median"]["total_step_ms"]["idx"],
+                "worst_total_step": ref_t["global"]["worst"]["total_step_ms"]["idx"]},
+        "aligned_window": {k: ref_t["data"]["aligned_window"][k] for k in ("steps_analyzed", "start_step", "end_step")},
+        "series": {"steps_checked": int(idx.size), "of": n, "mode": "all" if world == 1 else "stride+tail",
+                   "bit_equal": series_equal, "elements_differing": n_bad},
+        "per_rank_sums_bit_exact": bool(sums_bit_exact),
+        "mismatches": bad[:8], "seconds": time.perf_counter() - t0,
+    }
+
+
+def default_window_leg(rank, local, world, device, comm):
+    """The reference's default window (W = 10^4) on the seed the reference arm uses: this engine's
+    time per reduce and -- on rank 0, in a separate process -- the UNMODIFIED reference's, with the
+    two summaries compared field by field."""
+    import replay
+    from traceml_b200 import sections
+    from traceml_b200.engine import Engine
+
+    recs = replay.make_step_replay("balanced", world, DEFAULT_W, seed=1, only_ranks=[rank])[rank]
+    procs = replay.make_proc_replay("normal", world, DEFAULT_PROC_ROWS, seed=1, only_ranks=[rank])[rank]
+    eng = Engine(device=local, rank=rank, world=world, ring_slots=int(DEFAULT_W * 1.5), proc_slots=4096)
+    eng.load_steps(recs); eng.load_procs(procs)
+    torch.cuda.synchronize(device)
+    summ = sections.SummaryEngine([eng], comm, ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=world)
+    for _ in range(5):
+        res = summ.build(DEFAULT_W, DEFAULT_W)
+    barrier(world); torch.cuda.synchronize(device)
+    n_it = 50
+    t0 = time.perf_counter()
+    for _ in range(n_it):
+        res = summ.build(DEFAULT_W, DEFAULT_W)
+    torch.cuda.synchronize(device)
+    ms = max_over_ranks((time.perf_counter() - t0) / n_it * 1e3, world, device)
+    out = None
+    if rank == 0:
+        mine = {"step_time": {"status": res["step_time"]["diagnosis"]["primary"]["status"], "global": res["step_time"]["global"]},
+                "step_memory": {"status": res["step_memory"]["diagnosis"]["primary"]["status"],
+                                "global": res["step_memory"]["global"]},
+                "process": {"status": res["process"]["primary"]["status"], "global": res["process"].get("global")}}
+        out = {"window": DEFAULT_W, "ranks": world, "ms": ms, "GBps": b_reduce(world, DEFAULT_W) / (ms * 1e-3) / 1e9,
+               "summary": summary_digest(mine), "same_config_as_reference_arm": True}
+        if ref_available():
+            dw = ref_leg(["--leg", "reduce", "--ranks", world, "--rows", DEFAULT_W, "--window", DEFAULT_W,
+                          "--steps", 1, "--warmup", 0, "--proc-rows", DEFAULT_PROC_ROWS])
+            if "error" in dw:
+                out["reference"] = dw
+            else:
+                out["reference"] = {"ms": dw["s_per_step_median"] * 1e3, "us_per_row": dw["us_per_row"],
+                                    "kind": "unmodified reference, baseline/_ref, separate process, 1 core"}
+                out["speedup_vs_reference"] = dw["s_per_step_median"] * 1e3 / ms
+                out["parity_vs_reference"] = compare_digests(out["summary"], summary_digest(dw["summary"]))
+    barrier(world)
+    eng.close()
+    return out
 
 
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--window", type=int, default=4_000_000, help="W: step records per rank")
     ap.add_argument("--sample", type=int, default=40_000, help="cpu-baseline rows per rank")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl", "a2a"])
     ap.add_argument("--no-overhead", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
 
@@ -432,6 +686,7 @@ def main():
     from traceml_b200.engine import Engine
     from traceml_b200.reduce import LocalComm, TorchDistComm
 
+    t_bench0 = time.perf_counter()
     W = int(args.window)
     R = world
     comm = TorchDistComm() if world > 1 else LocalComm()
@@ -441,7 +696,6 @@ def main():
     procs = replay.make_proc_replay("normal", R, 60_000, seed=1, only_ranks=[rank])[rank]
     host = torch.empty(W * 128, dtype=torch.uint8).pin_memory()
     host.numpy()[:] = recs.view(np.uint8).reshape(-1)
-    del recs
     eng = Engine(device=local, rank=rank, world=R, ring_slots=W, proc_slots=65_536)
     eng.load_procs(procs)
     stream = torch.cuda.current_stream(device)
@@ -487,6 +741,27 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
     ms_step = ms_total / args.steps
     value = b_reduce(R, W) / (ms_step * 1e-3) / 1e9
+    # a longer look at the same loop (>= 1 s), as a cross-check of the K-step figure
+    barrier(world); torch.cuda.synchronize(device)
+    n_sus = max(50, int(1000.0 / max(ms_step, 1e-3)))
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_sus):
+        res = summ.build(W, 60_000)
+    s1.record()
+    torch.cuda.synchronize(device)
+    sustained = {"steps": n_sus, "ms_per_step": max_over_ranks(s0.elapsed_time(s1), world, device) / n_sus}
+    barrier(world)
+
+    # ---- parity of THIS window against the numpy oracle (outside the timed region)
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(recs, res, W, rank, world, device, replay.PROC_RAM_TOTAL_BYTES)
+        except Exception as exc:  # noqa: BLE001 -- a failed check is reported, never hidden
+            parity = {"checked": False, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        barrier(world)
+    del recs
 
     # ---- roofline of the dominant kernels (per launch, this rank)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -549,37 +824,70 @@ def main():
            "d2h_bytes_per_step": (1_768 + (1_536 * R if R > 1 else 0)) * R,
            "ms_per_step": e2e_s * 1e3}
 
-    # ---- (3) per-step overhead leg
+    exchange_used = res["reduce"].exchange
+    diagnosis = res["step_time"]["diagnosis"]["primary"]["status"] if res["step_time"]["diagnosis"] else None
+    eng.close()
+
+    # ---- (3) the reference's default window, both arms, same seed
+    try:
+        default_window = default_window_leg(rank, local, world, device, comm)
+    except Exception as exc:  # noqa: BLE001
+        default_window = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    # ---- (4) per-step overhead leg (the reference's real trace_step: own process, rank 0, N = 1)
     overhead = None
     if not args.no_overhead:
-        eng.close()
         overhead = step_overhead(device, world, local)
+        if rank == 0 and world == 1 and ref_available():
+            from traceml_b200.runtime import shutdown_engine
 
-    # ---- (4) CPU baseline on a bounded sample (rank 0, N = 1 only)
+            shutdown_engine()
+            ro = ref_leg(["--leg", "overhead"])
+            overhead["reference"] = ro
+            for k in ("micro_mlp", "resnet18_b64"):
+                if k in ro and k in overhead:
+                    overhead[k]["reference_us"] = ro[k]["reference_us"]
+                    overhead[k]["reference_untraced_us"] = ro[k]["untraced_us"]
+                    overhead[k]["reference_overhead_us"] = ro[k]["reference_overhead_us"]
+
+    # ---- (5) CPU baseline on a bounded sample (rank 0, N = 1 only): the unmodified reference
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        once = oracle_reduce_sample(1, args.sample)
-        once()
-        t = once()
-        cpu = {"value": b_reduce(1, args.sample) / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-               "sample": f"R=1 x W={args.sample} rows ({t:.2f} s, {t / args.sample * 1e6:.1f} us/row); "
-                         "oracle port of the reference's Python reduce, rows pre-parsed (no SQLite/JSON)",
-               "host_cores": os.cpu_count()}
+        if ref_available():
+            red = ref_leg(["--leg", "reduce", "--ranks", 1, "--rows", args.sample, "--steps", 3, "--warmup", 1,
+                           "--proc-rows", DEFAULT_PROC_ROWS])
+            if "error" not in red:
+                t = red["s_per_step_median"]
+                cpu = {"value": b_reduce(1, args.sample) / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference",
+                       "sample": f"R=1 x W={args.sample} rows of the same workload ({t:.2f} s/step, "
+                                 f"{red['us_per_row']:.1f} us/row): the UNMODIFIED reference's three summary sections "
+                                 "over SQLite written by its own projection writers (baseline/_ref, own process)",
+                       "host_cores": os.cpu_count(), "sqlite_projection": red["sqlite_projection"]}
+            else:
+                cpu = {"error": red["error"], "kind": "reference"}
+        if cpu is None or "error" in cpu:
+            once = oracle_reduce_sample(1, args.sample)
+            once()
+            t = once()
+            cpu = {"value": b_reduce(1, args.sample) / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                   "sample": f"R=1 x W={args.sample} rows ({t:.2f} s, {t / args.sample * 1e6:.1f} us/row); "
+                             "oracle port of the reference's Python reduce, rows pre-parsed (no SQLite/JSON)",
+                   "host_cores": os.cpu_count()}
 
     if rank == 0:
-        st = res["step_time"]["diagnosis"]
         line = {
             "metric": "cross_rank_reduce_GBps", "value": value, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": dict(workload_config(R, W), exchange=res["reduce"].exchange),
+            "config": workload_config(R, W), "exchange": exchange_used,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "records_per_s": R * W / (ms_step * 1e-3),
+            "records_per_s": R * W / (ms_step * 1e-3), "sustained": sustained,
+            "parity": parity, "default_window": default_window,
             "scaling_note": "weak: every rank holds W records; by the SURVEY formula the bytes grow as "
                             "(64 R + 128) W, so constant step time gives value(N)/value(1) = (64 N + 128)/192",
             "roofline": roofline, "cpu_baseline": cpu, "step_overhead": overhead,
-            "diagnosis": st["primary"]["status"] if st else None,
+            "diagnosis": diagnosis, "bench_wall_s": time.perf_counter() - t_bench0,
         }
         print(json.dumps(line))
     if world > 1:
