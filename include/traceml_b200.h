@@ -562,6 +562,16 @@ typedef struct tml_sections_args {
 int tml_sections_json(const tml_reduce_run_out* run, const tml_sections_args* args,
                       char* json_out, size_t cap);
 
+/* ---------------------------------------------------------------- TEST HOOK
+ * Host emulation of K3e -- the reference-order window sums (``s += x`` per row:
+ * reporting/sections/step_time/model.py:262-268, alignment.py:59-75) computed as composed
+ * integer maps, csrc/tml_exact_sum.h -- for one chain of non-negative doubles.  Runs the same
+ * plan / compose / verified-apply / tile-fallback steps as the kernels, serially, so the CPU
+ * suite can fuzz the arithmetic against a plain sequential loop.  ``planned`` = 0 skips the
+ * plan (every tile composed under the true exponent); ``slow_rows`` = rows that needed a real
+ * dependent add.  Never called by the product.                                           */
+int tml_xs_host_sum(const double* x, uint64_t n, int planned, double* out_sum, uint64_t* slow_rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,76 @@
+"""K3e arithmetic (csrc/tml_exact_sum.h) on the CPU: the reference's sequential ``s += x`` sums
+reproduced BIT FOR BIT from composed integer maps -- plan, chunk / group composition, verified
+application, 32-row tile fallback -- fuzzed against a plain sequential loop through the host
+emulation ``tml_xs_host_sum`` (the kernels share the header; GPU runs: test_gpu_parity_holes.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from traceml_b200 import _abi
+
+
+def xs(x, planned=1):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out, slow = C.c_double(), C.c_uint64()
+    rc = _abi.lib().tml_xs_host_sum(x.ctypes.data, len(x), planned, C.byref(out), C.byref(slow))
+    assert rc == 0
+    return out.value, slow.value
+
+
+def seq(x):
+    x = np.asarray(x, dtype=np.float64)
+    return float(np.add.accumulate(x)[-1]) if len(x) else 0.0
+
+
+def make(kind, n, rng):
+    if kind == 0:
+        return rng.integers(1, 40_000_000, n).astype(np.float64) / 1e6         # ns / 1e6: the real shape
+    if kind == 1:
+        return rng.uniform(0, 1, n) * 10.0 ** rng.integers(-12, 12, n)        # 24 decades of range
+    if kind == 2:
+        return rng.integers(0, 5, n).astype(np.float64) * 2.0 ** int(rng.integers(-3, 3))  # ties everywhere
+    if kind == 3:
+        return np.where(rng.uniform(size=n) < 0.5, 0.0, rng.uniform(0, 50, n))  # half the rows unused (+0.0)
+    if kind == 4:
+        return np.full(n, 0.5 ** int(rng.integers(0, 60)))                      # constant power of two
+    if kind == 5:
+        return rng.integers(0, 2 ** 20, n).astype(np.float64) * 2.0 ** -30 + 1.0
+    if kind == 6:
+        return np.concatenate([[1e18], rng.uniform(0, 1e3, n)])                 # one giant, then dust
+    return rng.lognormal(2, 3, n)
+
+
+@pytest.mark.parametrize("kind", range(8))
+def test_bit_exact_against_sequential_loop(kind):
+    rng = np.random.default_rng(100 + kind)
+    for _ in range(40):
+        n = int(rng.integers(1, 30_000))
+        x = make(kind, n, rng)
+        ref = seq(x)
+        for planned in (0, 1):
+            got, _ = xs(x, planned)
+            assert got == ref, (kind, n, planned, got, ref)
+
+
+def test_bench_sized_chain_needs_almost_no_sequential_adds():
+    rng = np.random.default_rng(7)
+    x = rng.integers(30_000_000, 45_000_000, 4_000_000).astype(np.float64) / 1e6
+    got, slow = xs(x, 1)
+    assert got == seq(x)
+    assert slow <= 64 * 32, slow   # one 32-row tile per binade crossing (~26 of them) + start-up
+
+
+def test_python_loop_is_the_same_thing():
+    """np.add.accumulate == the reference's Python ``s += x`` loop (the oracle's own pin)."""
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0, 40, 50_000)
+    s = 0.0
+    for v in x.tolist():
+        s += v
+    assert seq(x) == s == xs(x)[0]
+
+
+def test_empty_and_zero_chains():
+    assert xs(np.zeros(0))[0] == 0.0
+    assert xs(np.zeros(5000)) == (0.0, 0)

@@ -183,7 +183,8 @@ def test_native_sampler_fields_vs_psutil(cuda):
     """a9, native 1 kHz thread: RSS / allocator counters / total / cores equal the reference's
     sources; cpu_pct is the same estimator psutil uses -- (process user+sys CPU time delta) /
     (wall delta) x 100, not normalised by core count -- taken over the sampler's own period, so
-    its WINDOW MEAN is compared with psutil over the same window."""
+    its WINDOW MEAN is compared with psutil over the same window.  Rows are taken as the wire
+    rows the runtime hands to its sinks (samplers/schema/process.py:139-150)."""
     import psutil
 
     import traceml_b200 as traceml
@@ -196,7 +197,9 @@ def test_native_sampler_fields_vs_psutil(cuda):
     eng.proc_drain()
     proc = psutil.Process(os.getpid())
     keep = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
-    rt = TraceMLRuntime(interval_sec=0.05, native_process_hz=500.0)
+    rows = []
+    rt = TraceMLRuntime(interval_sec=0.05, native_process_hz=500.0,
+                        sinks=[lambda kind, r: rows.extend(r) if kind == "process" else None])
     proc.cpu_percent(interval=None)
     rt.start()
     t0 = time.perf_counter()
@@ -207,16 +210,20 @@ def test_native_sampler_fields_vs_psutil(cuda):
     rss = proc.memory_info().rss
     rt.stop()
     torch.cuda.synchronize()
-    recs, _ = eng.proc_drain()
-    assert len(recs) > 200
-    last = recs[-1]
-    assert int(last["mem_alloc"]) == used and int(last["mem_resv"]) == resv
-    assert int(last["mem_total"]) == torch.cuda.get_device_properties(0).total_memory or \
-        abs(int(last["mem_total"]) - torch.cuda.get_device_properties(0).total_memory) < (1 << 30)
-    assert int(last["cpu_cores"]) == (psutil.cpu_count(logical=True) or 0)
-    assert abs(int(last["rss"]) - rss) <= 16 << 20
+    assert len(rows) > 200, len(rows)
+    last = rows[-1]
+    assert last["gpu"]["mem_used"] == float(used) and last["gpu"]["mem_reserved"] == float(resv)
+    total = torch.cuda.get_device_properties(0).total_memory
+    assert abs(last["gpu"]["mem_total"] - total) < (2 << 30)   # cudaMemGetInfo total vs device property
+    assert last["cpu_cores"] == (psutil.cpu_count(logical=True) or 0)
+    assert last["ram_total"] == float(psutil.virtual_memory().total)
+    assert last["gpu_count"] == torch.cuda.device_count() and last["gpu_available"] is True
+    assert last["pid"] == os.getpid()
+    assert abs(last["ram_used"] - rss) <= 16 << 20
+    seqs = [r["seq"] for r in rows]
+    assert seqs == list(range(seqs[0], seqs[0] + len(seqs)))
     # window mean of the native estimator vs psutil over (almost) the same window
-    mean_native = float(np.mean(recs["cpu_pct"][5:]))
+    mean_native = float(np.mean([r["cpu"] for r in rows[5:]]))
     assert abs(mean_native - ps_cpu) < 35.0, (mean_native, ps_cpu)
     assert mean_native > 50.0
     del keep

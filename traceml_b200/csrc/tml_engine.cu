@@ -103,6 +103,8 @@ struct WinAcc {  // integer side results of k_window_rows (atomics; order-indepe
   u64 dups;
   u64 t_count;
   u64 n_both;  // rows that are candidates of BOTH kinds (time == memory window test)
+  u64 msum[2]; // exact sum of peak_alloc / peak_resv over the window rows (byte counts are integers;
+               // the reference's mean is CPython's compensated sum = the correctly rounded exact sum)
 };
 
 // ------------------------------------------------------------------ device helpers
@@ -416,7 +418,8 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
 
   u64 a_lo0 = ~0ull, a_lo1 = ~0ull, a_hi0 = 0, a_hi1 = 0, a_latest = 0;
   u32 a_nc0 = 0, a_nc1 = 0, a_nr0 = 0, a_nr1 = 0, a_viol = 0, a_dups = 0, a_tc = 0, a_both = 0;
-  double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 7 time sums + sum alloc, sum resv (window rows)
+  u64 a_sa = 0, a_sr = 0;                        // exact integer byte sums (window rows)
+  double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // 7 time sums (tree order) + 2 unused columns
   double mx_a = -INFINITY, mx_r = -INFINITY;      // rank peaks over the window rows
   const u64 nwt = (n + 31) / 32;
   const u64 wstride = (u64)gridDim.x * WR_WARPS;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
         ++a_tc;
       }
       if (in_time) {
-        sums[7] += (double)pa; sums[8] += (double)pr;
+        a_sa += pa; a_sr += pr;
         mx_a = fmax(mx_a, (double)pa); mx_r = fmax(mx_r, (double)pr);
       }
 
@@ -555,6 +558,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       t = __shfl_xor_sync(0xffffffffu, a_hi0, m); a_hi0 = t > a_hi0 ? t : a_hi0;
       t = __shfl_xor_sync(0xffffffffu, a_hi1, m); a_hi1 = t > a_hi1 ? t : a_hi1;
       t = __shfl_xor_sync(0xffffffffu, a_latest, m); a_latest = t > a_latest ? t : a_latest;
+      a_sa += __shfl_xor_sync(0xffffffffu, a_sa, m); a_sr += __shfl_xor_sync(0xffffffffu, a_sr, m);
     }
     a_nc0 = __reduce_add_sync(0xffffffffu, a_nc0); a_nc1 = __reduce_add_sync(0xffffffffu, a_nc1);
     a_nr0 = __reduce_add_sync(0xffffffffu, a_nr0); a_nr1 = __reduce_add_sync(0xffffffffu, a_nr1);
@@ -570,6 +574,8 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       if (a_dups) atomicAdd(&acc->dups, (u64)a_dups);
       if (a_tc) atomicAdd(&acc->t_count, (u64)a_tc);
       if (a_both) atomicAdd(&acc->n_both, (u64)a_both);
+      if (a_sa) atomicAdd(&acc->msum[0], a_sa);
+      if (a_sr) atomicAdd(&acc->msum[1], a_sr);
     }
   }
   __syncthreads();
@@ -737,13 +743,15 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
                                                       tml_window_row* __restrict__ xrows,
                                                       const u32* __restrict__ noncontig,
                                                       long long dense_first,
-                                                      double* partials /* [grid][16] */) {
+                                                      double* partials /* [grid][16] */,
+                                                      u64* gacc /* [2]: exact byte sums (zeroed by the host) */) {
   __shared__ double s_part[GA_THREADS / 32][4][4];
   const uint4* rows4 = reinterpret_cast<const uint4*>(rows);
   uint4* x4 = reinterpret_cast<uint4*>(xrows);
   const int q = threadIdx.x & 3;
   const bool copy = (*noncontig) != 0u;
   double a0 = 0, a1 = 0, a2 = (q == 3) ? -INFINITY : 0.0, a3 = (q == 3) ? -INFINITY : 0.0;
+  u64 ua = 0, ub = 0;  // q == 3: integer byte counts, summed exactly
   const u64 nthreads = (u64)gridDim.x * GA_THREADS;
   const u64 work = nsel * 4ull;
   // every thread of a 4-lane group runs the same trip count (work is a multiple of 4)
@@ -775,7 +783,7 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
       a2 += traced;
       a3 += dl + traced;
     } else {
-      a0 += d.x; a1 += d.y;
+      ua += (u64)d.x; ub += (u64)d.y;  // integer-valued doubles < 2^53: the conversion is exact
       a2 = fmax(a2, d.x); a3 = fmax(a3, d.y);
     }
   }
@@ -788,8 +796,13 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
     double b2 = shfl_xor_f64(a2, m), b3 = shfl_xor_f64(a3, m);
     a2 = is_max ? fmax(a2, b2) : (a2 + b2);
     a3 = is_max ? fmax(a3, b3) : (a3 + b3);
+    ua += __shfl_xor_sync(0xffffffffu, ua, m); ub += __shfl_xor_sync(0xffffffffu, ub, m);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 3 && gacc) {  // order-independent: integer atomics
+    if (ua) atomicAdd(&gacc[0], ua);
+    if (ub) atomicAdd(&gacc[1], ub);
+  }
   if (lane < 4) {
     s_part[warp][lane][0] = a0; s_part[warp][lane][1] = a1;
     s_part[warp][lane][2] = a2; s_part[warp][lane][3] = a3;
@@ -808,86 +821,18 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
 }
 
 
-// ------------------------------------------------------------------ K3e: sequential sums
-// Per-rank window means feed rank-level tie-breaks (closest-rank-to-median, argmax)
-// that the reference decides on the last ulp, so for windows up to
-// TML_EXACT_SUM_MAX rows the seven sums are recomputed in the reference's own
-// order -- newest row first, one IEEE add after another (model.py:262-268,
-// alignment.py:59-75) -- by one warp: lane k owns metric k's dependency chain,
-// every lane reads the same row (a broadcast load).  ~10 cycles per row.
+// ------------------------------------------------------------------ K3e: reference-order sums
+// Per-rank window means feed rank-level tie-breaks (closest-rank-to-median, argmax) that the
+// reference decides on the last ulp, so the seven sums are reproduced in the reference's own
+// order -- newest row first, one IEEE add after another (model.py:262-268, alignment.py:59-75)
+// -- bit for bit.  Round 1 did that with one dependent DADD chain (10 ns/row, usable up to 2^17
+// rows); tml_exact_sum.cuh does it for any window as composed integer maps.  A single-rank
+// engine (world == 1) has nobody to break a tie against: above TML_EXACT_SUM_MAX rows it keeps
+// the deterministic tree sums of K3a (rel <= 1e-13) and skips the two extra passes over its rows.
 
 #define TML_EXACT_SUM_MAX (1u << 17)
 
-#define SQ_THREADS 256
-// Reference-order sums: the seven per-rank sums as ONE IEEE add after another, newest row
-// first, exactly like the reference's Python loop -- rank tie-breaks downstream are decided
-// on their last ulp.  The adds cannot be reordered, but everything else can be taken off
-// the chain: the block streams 256-row tiles into shared memory with cp.async (double
-// buffered), all 256 threads derive their row's seven addends in parallel, and lanes 0..6 of
-// warp 0 then do exactly one dependent DADD per row.  (ncu r01: the first version -- loads
-// and the derived values inside the serial loop, one warp, five divergent paths per row --
-// took 394 ns/row, 3.9 ms at the default W = 10^4; this one takes 10 ns/row.)
-__global__ void __launch_bounds__(SQ_THREADS) k_seq_sums(const tml_window_row* __restrict__ rows,
-                                                         const u8* __restrict__ flags, u32 need,
-                                                         long long first, long long last, int aligned,
-                                                         const tml_window_row* __restrict__ xrows,
-                                                         const u32* __restrict__ noncontig,
-                                                         const u32* __restrict__ sel_rows,
-                                                         long long dense_first,
-                                                         double* __restrict__ out) {
-  __shared__ __align__(16) double raw[2][SQ_THREADS][8];
-  __shared__ __align__(16) double pre[SQ_THREADS][8];
-  const int tid = threadIdx.x;
-  // aligned mode: the aligned rows are either the gathered copy or a contiguous slice
-  if (aligned) {
-    if (dense_first >= 0) rows = rows + dense_first;
-    else rows = (*noncontig) ? xrows : (rows + sel_rows[0]);
-  }
-  const long long n = last - first + 1;
-  const long long ntiles = n > 0 ? (n + SQ_THREADS - 1) / SQ_THREADS : 0;
-  auto issue = [&](long long t, int buf) {  // tile t: rows last - t*256 - k, k = 0..255 (descending)
-    const long long i = last - t * SQ_THREADS - tid;
-    if (i >= first) {
-      const uint4* src = reinterpret_cast<const uint4*>(rows + i);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) cp_async16(&raw[buf][tid][q * 2], src + q);
-    }
-  };
-  double acc = 0.0;
-  if (ntiles) issue(0, 0);
-  cp_async_commit();
-  for (long long t = 0; t < ntiles; ++t) {
-    const int buf = (int)(t & 1);
-    if (t + 1 < ntiles) issue(t + 1, buf ^ 1);
-    cp_async_commit();
-    const long long i = last - t * SQ_THREADS - tid;
-    const bool live = i >= first;
-    const bool use = live && (flags ? ((flags[i] & need) == need) : true);
-    cp_async_wait<1>();  // this thread's part of tile t has landed
-    if (live) {          // a thread derives the addends of the row it fetched itself
-      const double* r = raw[buf][tid];
-      const double dl = r[0], fwd = r[2], bwd = r[3], opt = r[4], wall = r[5];
-      const double compute = (fwd + bwd) + opt;
-      const double traced = fmax(wall, compute);
-      double* o = pre[tid];
-      // + 0.0 leaves a non-negative running sum unchanged: unused rows add zeros
-      o[0] = use ? dl : 0.0; o[1] = use ? fwd : 0.0; o[2] = use ? bwd : 0.0; o[3] = use ? opt : 0.0;
-      o[4] = use ? (aligned ? fmax(0.0, traced) : wall) : 0.0;
-      o[5] = use ? traced : 0.0;
-      o[6] = use ? dl + traced : 0.0;
-    }
-    __syncthreads();
-    if (tid < 7) {
-      const long long left = n - t * SQ_THREADS;
-      const int cnt = left < SQ_THREADS ? (int)left : SQ_THREADS;
-#pragma unroll 8
-      for (int k = 0; k < cnt; ++k) acc += pre[k][tid];  // the chain: one DADD per row
-    }
-    __syncthreads();  // pre and raw[buf] are free again
-  }
-  cp_async_wait<0>();
-  if (tid < 7) out[tid] = acc;
-}
+#include "tml_exact_sum.cuh"
 
 // ------------------------------------------------------------------ K4: window reduce
 
@@ -1268,6 +1213,12 @@ struct tml_ctx {
   double* d_pfinal = nullptr;
   bool proc_pending = false;
   u64 proc_pending_n = 0;
+  u64* d_gacc = nullptr;         // k_gather's exact byte sums
+  // K3e workspace (tml_exact_sum.cuh)
+  u64 cap_xs = 0;                // chunks
+  double* d_xs_csum = nullptr; int* d_xs_plan = nullptr; void* d_xs_fn = nullptr;
+  void* d_xs_gfn = nullptr; int* d_xs_gplan = nullptr; double* d_xs_out = nullptr; u64* d_xs_stats = nullptr;
+  u64 xs_slow_rows = 0;          // rows the last K3e walk had to add one by one (diagnostic)
   double* d_partials = nullptr;  // max(grid) * 16 doubles
   double* d_final = nullptr;     // 64 doubles
   u64* d_bandcnt = nullptr;
@@ -1285,6 +1236,53 @@ static int grid_for(const tml_ctx* c, u64 work_items, int per_block) {
   u64 cap = (u64)c->n_sms * 4ull;  // persistent-style: a multiple of the SM count
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
+}
+
+// K3e launcher: the seven sums of `src` in reference order -> d_out[0..7) (device), on stream s.
+static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaStream_t s) {
+  const long long n = src.last - src.first + 1;
+  if (n <= 0) { CK(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), s)); return TML_OK; }
+  const long long nchunks = (n + XS_CHUNK - 1) / XS_CHUNK, ngroups = (nchunks + XS_GROUP - 1) / XS_GROUP;
+  const int planned = n > 2048 ? 1 : 0;  // tiny windows: the walk composes every tile itself
+  if ((u64)nchunks > c->cap_xs || !c->d_xs_csum) {
+    cudaFree(c->d_xs_csum); cudaFree(c->d_xs_plan); cudaFree(c->d_xs_fn); cudaFree(c->d_xs_gfn); cudaFree(c->d_xs_gplan);
+    c->d_xs_csum = nullptr; c->d_xs_plan = nullptr; c->d_xs_fn = nullptr; c->d_xs_gfn = nullptr; c->d_xs_gplan = nullptr;
+    c->cap_xs = 0;
+    const u64 cap = (u64)nchunks + (u64)nchunks / 4 + 64, gcap = (cap + XS_GROUP - 1) / XS_GROUP + 1;
+    CK(cudaMalloc(&c->d_xs_csum, cap * 8 * sizeof(double)));
+    CK(cudaMalloc(&c->d_xs_plan, cap * 8 * sizeof(int)));
+    CK(cudaMalloc(&c->d_xs_fn, cap * 7 * sizeof(XsFn)));
+    CK(cudaMalloc(&c->d_xs_gfn, gcap * 7 * sizeof(XsFn)));
+    CK(cudaMalloc(&c->d_xs_gplan, gcap * 8 * sizeof(int)));
+    c->cap_xs = cap;
+  }
+  if (planned) {
+    const long long cap_grid = (long long)c->n_sms * 8;
+    const int grid = (int)(nchunks < cap_grid ? nchunks : cap_grid);
+    k_xs_partial<<<grid, XS_CHUNK, 0, s>>>(src, n, nchunks, c->d_xs_csum);
+    CK(cudaPeekAtLastError());
+    k_xs_plan<<<1, 1024, 0, s>>>(c->d_xs_csum, nchunks, c->d_xs_plan);
+    CK(cudaPeekAtLastError());
+    k_xs_compose<<<grid, XS_CHUNK, 0, s>>>(src, n, nchunks, c->d_xs_plan, (XsFn*)c->d_xs_fn);
+    CK(cudaPeekAtLastError());
+    k_xs_groups<<<(int)((ngroups * 7 + 7) / 8), 256, 0, s>>>((const XsFn*)c->d_xs_fn, c->d_xs_plan, nchunks, ngroups,
+                                                             (XsFn*)c->d_xs_gfn, c->d_xs_gplan);
+    CK(cudaPeekAtLastError());
+    c->launches += 4;
+  }
+  k_xs_walk<<<1, 7 * 32, 0, s>>>(src, n, nchunks, ngroups, (const XsFn*)c->d_xs_fn, c->d_xs_plan,
+                                 (const XsFn*)c->d_xs_gfn, c->d_xs_gplan, planned, d_out, c->d_xs_stats);
+  CK(cudaPeekAtLastError());
+  c->launches += 1;
+  return TML_OK;
+}
+
+static XsSrc xs_window_src(const tml_ctx* c, long long first, long long last) {
+  XsSrc x;
+  memset(&x, 0, sizeof(x));
+  x.rows = c->d_rows; x.flags = c->d_flags; x.need = RF_USABLE | RF_IN_TIME;
+  x.first = first; x.last = last; x.aligned = 0; x.dense_first = -1;
+  return x;
 }
 
 extern "C" {
@@ -1333,6 +1331,9 @@ int tml_init(int device, int rank, int world, uint32_t ring_slots, uint32_t proc
   CK(cudaHostGetDevicePointer((void**)&c->d_pmirror, c->h_pmirror, 0));
   CK(cudaMalloc(&c->d_total, sizeof(u64)));
   CK(cudaMalloc(&c->d_noncontig, sizeof(u32)));
+  CK(cudaMalloc(&c->d_gacc, 2 * sizeof(u64)));
+  CK(cudaMalloc(&c->d_xs_out, 16 * sizeof(double)));
+  CK(cudaMalloc(&c->d_xs_stats, 8 * sizeof(u64)));
   CK(cudaMalloc(&c->d_partials, (size_t)c->n_sms * 4 * 16 * sizeof(double)));
   CK(cudaMalloc(&c->d_final, 64 * sizeof(double) + sizeof(WinAcc)));
   c->d_winacc = reinterpret_cast<WinAcc*>(c->d_final + 64);  // one D2H copy fetches both
@@ -1354,7 +1355,9 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_rows); cudaFree(c->d_steps); cudaFree(c->d_flags);
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_rowof[k]); cudaFree(c->d_xrows[k]); }
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
-  cudaFree(c->d_noncontig);
+  cudaFree(c->d_noncontig); cudaFree(c->d_gacc);
+  cudaFree(c->d_xs_csum); cudaFree(c->d_xs_plan); cudaFree(c->d_xs_fn); cudaFree(c->d_xs_gfn);
+  cudaFree(c->d_xs_gplan); cudaFree(c->d_xs_out); cudaFree(c->d_xs_stats);
   cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
   cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
@@ -1639,12 +1642,10 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
   CK(cudaPeekAtLastError());
   c->launches += 2;  // K3a + its finalize
-  const bool exact_win = (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
+  const bool exact_win = c->world > 1 || (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
   if (exact_win) {  // reference-order sums (used instead of the tree sums)
-    k_seq_sums<<<1, SQ_THREADS, 0, s>>>(c->d_rows, c->d_flags, RF_USABLE | RF_IN_TIME, (long long)c->win_tstart,
-                                (long long)n - 1, 0, nullptr, nullptr, nullptr, -1ll, c->d_final);
-    CK(cudaPeekAtLastError());
-    c->launches += 1;
+    int xr = launch_exact_sums(c, xs_window_src(c, (long long)c->win_tstart, (long long)n - 1), c->d_final, s);
+    if (xr != TML_OK) return xr;
   }
   // d_final[0..7) exact sums | d_final[32..43) tree sums + maxima | d_final[64..] WinAcc: one copy
   char* st = (char*)c->h_stage;
@@ -1657,6 +1658,8 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   memcpy(&acc, st, sizeof(acc));
   memcpy(out->t_sums, st + 256, 7 * sizeof(double));
   memcpy(c->win_msums, st + 320, 4 * sizeof(double));
+  c->win_msums[0] = (double)acc.msum[0];  // exact integer sums, rounded once (u64 -> f64 is RN)
+  c->win_msums[1] = (double)acc.msum[1];
   memcpy(c->win_tsums, out->t_sums, 7 * sizeof(double));
   out->latest_step = acc.latest_step;
   out->monotone = acc.violations == 0 ? 1u : 0u;
@@ -1758,21 +1761,25 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   CK(cudaMemsetAsync(c->d_noncontig, 0, sizeof(u32), s));
   k_check_contig<<<grid_for(c, keep, 256), 256, 0, s>>>(c->d_selrow, keep, c->d_noncontig);
   CK(cudaPeekAtLastError());
+  CK(cudaMemsetAsync(c->d_gacc, 0, 2 * sizeof(u64), s));
   k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, c->d_selrow, keep, c->d_xrows[kind], c->d_noncontig,
-                                       -1ll, c->d_partials);
+                                       -1ll, c->d_partials, c->d_gacc);
   CK(cudaPeekAtLastError());
   c->launches += 1;
   k_finalize<<<1, 32 * 16, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
   CK(cudaPeekAtLastError());
   c->launches += 2;
-  const bool exact = (kind == TML_KIND_TIME) && keep <= TML_EXACT_SUM_MAX;
+  const bool exact = (kind == TML_KIND_TIME) && (c->world > 1 || keep <= TML_EXACT_SUM_MAX);
   if (exact) {
-    k_seq_sums<<<1, SQ_THREADS, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)keep - 1, 1, c->d_xrows[kind],
-                                c->d_noncontig, c->d_selrow, -1ll, c->d_final + 16);
-    CK(cudaPeekAtLastError());
-    c->launches += 1;
+    XsSrc x;
+    memset(&x, 0, sizeof(x));
+    x.rows = c->d_rows; x.first = 0; x.last = (long long)keep - 1; x.aligned = 1;
+    x.xrows = c->d_xrows[kind]; x.noncontig = c->d_noncontig; x.sel_rows = c->d_selrow; x.dense_first = -1;
+    int xr = launch_exact_sums(c, x, c->d_final + 16, s);
+    if (xr != TML_OK) return xr;
     CK(cudaMemcpyAsync(st + 320, c->d_final + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
+  CK(cudaMemcpyAsync(st + 400, c->d_gacc, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 64, c->d_final, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 256, c->d_selstep, sizeof(u64), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 264, c->d_selstep + (keep - 1), sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -1791,6 +1798,11 @@ int tml_win_select(tml_ctx* c, uint32_t kind, uint64_t glo, uint64_t span, const
   out->t_sums[0] = f[0]; out->t_sums[1] = f[4]; out->t_sums[2] = f[5]; out->t_sums[3] = f[8];
   out->t_sums[4] = f[9]; out->t_sums[5] = f[10]; out->t_sums[6] = f[11];
   out->m_sums[0] = f[12]; out->m_sums[1] = f[13]; out->m_sums[2] = f[14]; out->m_sums[3] = f[15];
+  {
+    u64 g[2];
+    memcpy(g, st + 400, sizeof(g));
+    out->m_sums[0] = (double)g[0]; out->m_sums[1] = (double)g[1];  // exact integer sums, rounded once
+  }
   if (exact) memcpy(out->t_sums, st + 320, 7 * sizeof(double));
   memcpy(&out->start_step, st + 256, sizeof(u64));
   memcpy(&out->end_step, st + 264, sizeof(u64));
@@ -1828,21 +1840,25 @@ int tml_win_select_dense(tml_ctx* c, uint32_t kind, uint64_t first_step, uint64_
   }
   const int grid = grid_for(c, n_common * 4, GA_THREADS);
   CK(cudaMemsetAsync(c->d_noncontig, 0, sizeof(u32), s));
+  CK(cudaMemsetAsync(c->d_gacc, 0, 2 * sizeof(u64), s));
   k_gather<<<grid, GA_THREADS, 0, s>>>(c->d_rows, nullptr, n_common, nullptr, c->d_noncontig,
-                                       (long long)first_row, c->d_partials);
+                                       (long long)first_row, c->d_partials, c->d_gacc);
   CK(cudaPeekAtLastError());
   k_finalize<<<1, 32 * 16, 0, s>>>(c->d_partials, grid, 16, (1u << 14) | (1u << 15), c->d_final);
   CK(cudaPeekAtLastError());
   c->launches += 2;
-  const bool exact = (kind == TML_KIND_TIME) && n_common <= TML_EXACT_SUM_MAX;
+  const bool exact = (kind == TML_KIND_TIME) && (c->world > 1 || n_common <= TML_EXACT_SUM_MAX);
   char* st = (char*)c->h_stage;
   if (exact) {
-    k_seq_sums<<<1, SQ_THREADS, 0, s>>>(c->d_rows, nullptr, 0u, 0ll, (long long)n_common - 1, 1, nullptr, nullptr,
-                                nullptr, (long long)first_row, c->d_final + 16);
-    CK(cudaPeekAtLastError());
-    c->launches += 1;
+    XsSrc x;
+    memset(&x, 0, sizeof(x));
+    x.rows = c->d_rows; x.first = 0; x.last = (long long)n_common - 1; x.aligned = 1;
+    x.dense_first = (long long)first_row;
+    int xr = launch_exact_sums(c, x, c->d_final + 16, s);
+    if (xr != TML_OK) return xr;
     CK(cudaMemcpyAsync(st + 320, c->d_final + 16, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
+  CK(cudaMemcpyAsync(st + 400, c->d_gacc, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(st + 64, c->d_final, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   double f[16];
@@ -1850,6 +1866,11 @@ int tml_win_select_dense(tml_ctx* c, uint32_t kind, uint64_t first_step, uint64_
   out->t_sums[0] = f[0]; out->t_sums[1] = f[4]; out->t_sums[2] = f[5]; out->t_sums[3] = f[8];
   out->t_sums[4] = f[9]; out->t_sums[5] = f[10]; out->t_sums[6] = f[11];
   out->m_sums[0] = f[12]; out->m_sums[1] = f[13]; out->m_sums[2] = f[14]; out->m_sums[3] = f[15];
+  {
+    u64 g[2];
+    memcpy(g, st + 400, sizeof(g));
+    out->m_sums[0] = (double)g[0]; out->m_sums[1] = (double)g[1];  // exact integer sums, rounded once
+  }
   if (exact) memcpy(out->t_sums, st + 320, 7 * sizeof(double));
   out->start_step = first_step;
   out->end_step = first_step + n_common - 1;
