@@ -217,6 +217,17 @@ typedef struct tml_win_info {
  * load_step_time_section_data / build_rank_summary and the candidate query of
  * the step-memory loader: reporting/sections/step_time/loader.py:44-72,
  * step_time/model.py:162-281, step_memory/loader.py:112-205. */
+/* Reference-order sums (K3e, csrc/tml_exact_sum.h) may run BESIDE the row exchange instead of in
+ * front of it: with ``on`` != 0 tml_win_prepare launches them on the context's side stream and
+ * returns the deterministic tree sums in tml_win_info.t_sums; tml_win_exact_collect then yields
+ * the reference-order sums (model.py:262-268 order) once they are needed -- at the end of the
+ * reduce, for the per-rank summaries and the rank tie-breaks.  Off by default (stage-by-stage
+ * callers get exact sums directly).                                                       */
+int tml_win_set_defer(tml_ctx* ctx, int on);
+int tml_win_exact_collect(tml_ctx* ctx, void* stream, double t_sums[7]);
+/* rows the last K3e walk had to add one by one, per chain (diagnostic) */
+int tml_win_exact_stats(tml_ctx* ctx, uint64_t slow_rows[7]);
+
 int tml_win_prepare(tml_ctx* ctx, uint32_t window, void* stream,
                     tml_win_info* out);
 

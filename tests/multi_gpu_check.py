@@ -88,6 +88,21 @@ def main():
                     pref = process_oracle.process_section(oracle_proc_rows(procs_all, world), max_rows=W)
                     assert_struct(plain(a["process"]["primary"]), plain(pref["diagnosis"]["primary"]), "proc.primary")
                 else:
+                    # large window: the numpy oracle (pinned == row-level oracle == reference); the
+                    # per-rank sums must be BIT-exact (K3e, deferred beside K4 in the native driver)
+                    from oracle import fast_oracle
+
+                    big = replay.make_step_replay(scenario, world, S, seed=11)
+                    fref = fast_oracle.step_time_section(big, max_rows=W)
+                    g = a["step_time"]
+                    assert plain(g["data"]["aligned_summary"]) == plain(fref["data"]["aligned_summary"]), "aligned sums"
+                    assert plain(g["data"]["per_global_rank_summary"]) == plain(fref["data"]["per_global_rank_summary"])
+                    assert_struct(plain(g["diagnosis"]), plain(fref["diagnosis"]), "big.diagnosis")
+                    assert_struct(plain(g["global"]), plain(fref["global"]), "big.global")
+                    mref = fast_oracle.step_memory_section(big, window_size=W,
+                                                           gpu_total_bytes=a["step_memory"]["gpu_total_bytes"])
+                    assert plain(a["step_memory"]["per_global_rank"]) == plain(mref["per_global_rank"])
+                    assert_struct(plain(a["step_memory"]["global"]), plain(mref["global"]), "big.mem.global")
                     assert a["step_time"]["diagnosis"]["primary"]["kind"] == "INPUT_STRAGGLER"
                     assert a["step_time"]["data"]["aligned_window"]["steps_analyzed"] == W
                 print(f"[multi_gpu_check] {scenario} R={world} W={W}: OK "

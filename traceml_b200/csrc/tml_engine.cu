@@ -1216,9 +1216,12 @@ struct tml_ctx {
   u64* d_gacc = nullptr;         // k_gather's exact byte sums
   // K3e workspace (tml_exact_sum.cuh)
   u64 cap_xs = 0;                // chunks
-  double* d_xs_csum = nullptr; int* d_xs_plan = nullptr; void* d_xs_fn = nullptr;
-  void* d_xs_gfn = nullptr; int* d_xs_gplan = nullptr; double* d_xs_out = nullptr; u64* d_xs_stats = nullptr;
-  u64 xs_slow_rows = 0;          // rows the last K3e walk had to add one by one (diagnostic)
+  void* d_xs_buf = nullptr;      // one allocation, carved into XsWork
+  XsWork xs_work;
+  double* d_xs_out = nullptr; u64* d_xs_stats = nullptr;
+  cudaStream_t xs_stream = nullptr;  // K3e beside K4 (tml_win_set_defer)
+  cudaEvent_t xs_gate = nullptr, xs_done = nullptr;
+  bool xs_defer = false, xs_pending = false;
   double* d_partials = nullptr;  // max(grid) * 16 doubles
   double* d_final = nullptr;     // 64 doubles
   u64* d_bandcnt = nullptr;
@@ -1241,37 +1244,50 @@ static int grid_for(const tml_ctx* c, u64 work_items, int per_block) {
 // K3e launcher: the seven sums of `src` in reference order -> d_out[0..7) (device), on stream s.
 static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaStream_t s) {
   const long long n = src.last - src.first + 1;
+  // one workspace per context: a job on another stream must wait for the deferred one
+  if (c->xs_pending && s != c->xs_stream) CK(cudaStreamWaitEvent(s, c->xs_done, 0));
   if (n <= 0) { CK(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), s)); return TML_OK; }
   const long long nchunks = (n + XS_CHUNK - 1) / XS_CHUNK, ngroups = (nchunks + XS_GROUP - 1) / XS_GROUP;
-  const int planned = n > 2048 ? 1 : 0;  // tiny windows: the walk composes every tile itself
-  if ((u64)nchunks > c->cap_xs || !c->d_xs_csum) {
-    cudaFree(c->d_xs_csum); cudaFree(c->d_xs_plan); cudaFree(c->d_xs_fn); cudaFree(c->d_xs_gfn); cudaFree(c->d_xs_gplan);
-    c->d_xs_csum = nullptr; c->d_xs_plan = nullptr; c->d_xs_fn = nullptr; c->d_xs_gfn = nullptr; c->d_xs_gplan = nullptr;
-    c->cap_xs = 0;
+  const int planned = n > 1024 ? 1 : 0;  // tiny windows: the walk adds / composes every tile itself
+  const int max_grid = c->n_sms * 4 < 1024 ? c->n_sms * 4 : 1024;
+  if ((u64)nchunks > c->cap_xs || !c->d_xs_buf) {
+    cudaFree(c->d_xs_buf);
+    c->d_xs_buf = nullptr; c->cap_xs = 0;
     const u64 cap = (u64)nchunks + (u64)nchunks / 4 + 64, gcap = (cap + XS_GROUP - 1) / XS_GROUP + 1;
-    CK(cudaMalloc(&c->d_xs_csum, cap * 8 * sizeof(double)));
-    CK(cudaMalloc(&c->d_xs_plan, cap * 8 * sizeof(int)));
-    CK(cudaMalloc(&c->d_xs_fn, cap * 7 * sizeof(XsFn)));
-    CK(cudaMalloc(&c->d_xs_gfn, gcap * 7 * sizeof(XsFn)));
-    CK(cudaMalloc(&c->d_xs_gplan, gcap * 8 * sizeof(int)));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_csum = take(cap * 8 * sizeof(double)), o_cpre = take(cap * 8 * sizeof(double));
+    const size_t o_btot = take(1024 * 8 * sizeof(double)), o_bpre = take(1024 * 8 * sizeof(double));
+    const size_t o_plan = take(cap * 8 * sizeof(int)), o_ea = take(cap * 8 * sizeof(int));
+    const size_t o_fn = take(cap * 7 * sizeof(XsFn)), o_gfn = take(gcap * 7 * sizeof(XsFn));
+    const size_t o_gplan = take(gcap * 8 * sizeof(int)), o_tiles = take((size_t)XS_SLOT_CAP * sizeof(XsTileMaps));
+    const size_t o_ns = take(256);
+    CK(cudaMalloc(&c->d_xs_buf, off));
+    char* base = (char*)c->d_xs_buf;
+    XsWork w;
+    w.csum = (double*)(base + o_csum); w.cpre = (double*)(base + o_cpre);
+    w.btot = (double*)(base + o_btot); w.bpre = (double*)(base + o_bpre);
+    w.plan = (int*)(base + o_plan); w.ea = (int*)(base + o_ea);
+    w.fn = (XsFn*)(base + o_fn); w.gfn = (XsFn*)(base + o_gfn); w.gplan = (int*)(base + o_gplan);
+    w.tiles = (XsTileMaps*)(base + o_tiles); w.nslots = (unsigned int*)(base + o_ns);
+    c->xs_work = w;
     c->cap_xs = cap;
   }
+  const XsWork& w = c->xs_work;
   if (planned) {
-    const long long cap_grid = (long long)c->n_sms * 8;
-    const int grid = (int)(nchunks < cap_grid ? nchunks : cap_grid);
-    k_xs_partial<<<grid, XS_CHUNK, 0, s>>>(src, n, nchunks, c->d_xs_csum);
+    const long long want = (nchunks + XS_WARPS - 1) / XS_WARPS;
+    const int grid = (int)(want < max_grid ? want : max_grid);
+    k_xs_partial<<<grid, XS_WARPS * 32, 0, s>>>(src, n, nchunks, w);
     CK(cudaPeekAtLastError());
-    k_xs_plan<<<1, 1024, 0, s>>>(c->d_xs_csum, nchunks, c->d_xs_plan);
+    k_xs_bscan<<<1, 1024, 0, s>>>(w, grid);
     CK(cudaPeekAtLastError());
-    k_xs_compose<<<grid, XS_CHUNK, 0, s>>>(src, n, nchunks, c->d_xs_plan, (XsFn*)c->d_xs_fn);
+    k_xs_compose<<<grid, XS_WARPS * 32, 0, s>>>(src, n, nchunks, w);
     CK(cudaPeekAtLastError());
-    k_xs_groups<<<(int)((ngroups * 7 + 7) / 8), 256, 0, s>>>((const XsFn*)c->d_xs_fn, c->d_xs_plan, nchunks, ngroups,
-                                                             (XsFn*)c->d_xs_gfn, c->d_xs_gplan);
+    k_xs_groups<<<(int)((ngroups * 7 + 7) / 8), 256, 0, s>>>(w, nchunks, ngroups);
     CK(cudaPeekAtLastError());
     c->launches += 4;
   }
-  k_xs_walk<<<1, 7 * 32, 0, s>>>(src, n, nchunks, ngroups, (const XsFn*)c->d_xs_fn, c->d_xs_plan,
-                                 (const XsFn*)c->d_xs_gfn, c->d_xs_gplan, planned, d_out, c->d_xs_stats);
+  k_xs_walk<<<1, 7 * 32, 0, s>>>(src, n, nchunks, ngroups, w, planned, d_out, c->d_xs_stats);
   CK(cudaPeekAtLastError());
   c->launches += 1;
   return TML_OK;
@@ -1356,8 +1372,10 @@ int tml_shutdown(tml_ctx* c) {
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_rowof[k]); cudaFree(c->d_xrows[k]); }
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
   cudaFree(c->d_noncontig); cudaFree(c->d_gacc);
-  cudaFree(c->d_xs_csum); cudaFree(c->d_xs_plan); cudaFree(c->d_xs_fn); cudaFree(c->d_xs_gfn);
-  cudaFree(c->d_xs_gplan); cudaFree(c->d_xs_out); cudaFree(c->d_xs_stats);
+  cudaFree(c->d_xs_buf); cudaFree(c->d_xs_out); cudaFree(c->d_xs_stats);
+  if (c->xs_stream) cudaStreamDestroy(c->xs_stream);
+  if (c->xs_gate) cudaEventDestroy(c->xs_gate);
+  if (c->xs_done) cudaEventDestroy(c->xs_done);
   cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
   cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
@@ -1607,7 +1625,16 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   out->n_retained = n;
   out->monotone = 1;
   c->win_ncand[0] = c->win_ncand[1] = 0;
-  if (n == 0) { c->win_ready = true; return TML_OK; }
+  if (c->xs_pending) {  // the previous reduce's K3e still reads the rows this call rewrites
+    CK(cudaStreamWaitEvent(s, c->xs_done, 0));
+    c->xs_pending = false;
+  }
+  if (n == 0) {
+    memset(c->win_tsums, 0, sizeof(c->win_tsums));
+    memset(c->win_msums, 0, sizeof(c->win_msums));
+    c->win_ready = true;
+    return TML_OK;
+  }
   int rc;
   u64 cap = c->cap_rows;
   if (n > cap) {
@@ -1642,8 +1669,24 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
   CK(cudaPeekAtLastError());
   c->launches += 2;  // K3a + its finalize
-  const bool exact_win = c->world > 1 || (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
-  if (exact_win) {  // reference-order sums (used instead of the tree sums)
+  bool exact_win = c->world > 1 || (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
+  if (exact_win && c->xs_defer) {
+    // beside the row exchange / K4: side stream, gated on K3a; the tree sums stand in until
+    // tml_win_exact_collect
+    if (!c->xs_stream) {
+      CK(cudaStreamCreateWithFlags(&c->xs_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->xs_gate, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->xs_done, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->xs_gate, s));
+    CK(cudaStreamWaitEvent(c->xs_stream, c->xs_gate, 0));
+    int xr = launch_exact_sums(c, xs_window_src(c, (long long)c->win_tstart, (long long)n - 1), c->d_xs_out,
+                               c->xs_stream);
+    if (xr != TML_OK) return xr;
+    CK(cudaEventRecord(c->xs_done, c->xs_stream));
+    c->xs_pending = true;
+    exact_win = false;
+  } else if (exact_win) {  // reference-order sums (used instead of the tree sums)
     int xr = launch_exact_sums(c, xs_window_src(c, (long long)c->win_tstart, (long long)n - 1), c->d_final, s);
     if (xr != TML_OK) return xr;
   }
@@ -1691,6 +1734,36 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   if (!out->monotone)
     return set_err(TML_ERR_NONMONOTONIC, "step ids decrease inside the retained ring (%llu places)",
                    acc.violations);
+  return TML_OK;
+}
+
+int tml_win_set_defer(tml_ctx* c, int on) {
+  if (!c) return TML_ERR_ARG;
+  c->xs_defer = on != 0;
+  return TML_OK;
+}
+
+int tml_win_exact_collect(tml_ctx* c, void* stream, double t_sums[7]) {
+  if (!c || !t_sums) return TML_ERR_ARG;
+  if (!c->win_ready) return set_err(TML_ERR_STATE, "tml_win_exact_collect before tml_win_prepare");
+  if (c->xs_pending) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamWaitEvent(s, c->xs_done, 0));
+    char* st = (char*)c->h_stage;
+    CK(cudaMemcpyAsync(st + 448, c->d_xs_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(c->win_tsums, st + 448, 7 * sizeof(double));
+    c->xs_pending = false;
+  }
+  memcpy(t_sums, c->win_tsums, 7 * sizeof(double));
+  return TML_OK;
+}
+
+int tml_win_exact_stats(tml_ctx* c, uint64_t slow_rows[7]) {
+  if (!c || !slow_rows) return TML_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpy(slow_rows, c->d_xs_stats, 7 * sizeof(u64), cudaMemcpyDeviceToHost));
   return TML_OK;
 }
 

@@ -107,6 +107,29 @@ XS_HD XsFn xs_compose(const XsFn& f, const XsFn& g) {
   return h;
 }
 
+// Hot-loop variants: no validity sentinel, no range check.  The caller tracks "some element was
+// invalid" separately (xs_elem_raw's return value) and bounds the magnitudes itself: a map of one
+// element is < 2^53, so 2^10 composed elements stay < 2^63.  Non-tie maps (c0 == c1, all but
+// ~2^-20 of the elements) compose by a plain add.
+XS_HD bool xs_elem_raw(double x, int eb, XsFn* out) {
+  const XsFn f = xs_elem(x, eb);
+  if (!xs_valid(f)) { *out = xs_identity(); return false; }
+  *out = f;
+  return true;
+}
+XS_HD XsFn xs_compose_raw(const XsFn& f, const XsFn& g) {
+  XsFn h;
+  if (g.c0 == g.c1) { h.c0 = f.c0 + g.c0; h.c1 = f.c1 + g.c0; return h; }
+  h.c0 = f.c0 + ((f.c0 & 1ull) ? g.c1 : g.c0);
+  h.c1 = f.c1 + (((1ull + f.c1) & 1ull) ? g.c1 : g.c0);
+  return h;
+}
+// close a raw composition: anything that could leave the binade (or saw an invalid element) is invalid
+XS_HD XsFn xs_seal(const XsFn& f, bool ok) {
+  if (!ok || f.c0 >= (1ull << 53) || f.c1 >= (1ull << 53)) return xs_invalid();
+  return f;
+}
+
 // Apply f (composed under biased exponent eb) to s.  False -- s untouched -- if s is not in that
 // binade, f is invalid, or the result would reach 2^(e+1) (then some add inside crossed, or would
 // round at a coarser ulp: the caller redoes those rows with real adds).

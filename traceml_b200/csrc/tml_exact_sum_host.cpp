@@ -26,10 +26,15 @@ extern "C" int tml_xs_host_sum(const double* x, uint64_t n, int planned, double*
     for (uint64_t c = 0; c < nchunks; ++c) {  // X3
       if (plan[c] == XS_PLAN_ZERO) { fn[c] = xs_identity(); continue; }
       if (plan[c] < 1) continue;
-      XsFn f = xs_identity();
+      XsFn f = xs_identity();  // the kernels' hot loop: raw compose, sealed once per chunk
+      bool ok = true;
       const uint64_t lo = c * XS_CHUNK, hi = lo + XS_CHUNK < n ? lo + XS_CHUNK : n;
-      for (uint64_t i = lo; i < hi; ++i) f = xs_compose(f, xs_elem(x[i], plan[c]));
-      fn[c] = f;
+      for (uint64_t i = lo; i < hi; ++i) {
+        XsFn g;
+        ok = xs_elem_raw(x[i], plan[c], &g) && ok;
+        f = xs_compose_raw(f, g);
+      }
+      fn[c] = xs_seal(f, ok);
     }
     for (uint64_t g = 0; g < ngroups; ++g) {  // X3b
       int emax = XS_PLAN_ZERO;

@@ -252,6 +252,7 @@ constexpr u64 P2P_MIN_ROWS = 1000000;  // reduce.py: one-shot IPC mapping (44-65
 struct KindState {
   tml_kind_result* res;
   std::vector<Aligned> blocks;  // by global rank (valid for ranks in res->used)
+  bool from_spec = false;       // aligned window == every rank's own window: aligned sums are window sums
 };
 
 u32 mode_for(const Run& r, u32 exchange, u64 n_common) {
@@ -324,8 +325,10 @@ int align_kind(Run& r, u32 kind, u32 window, u32 exchange, const tml_win_info* i
   if (all_dense) {
     bool same_window = spec_all != nullptr && span <= window;
     for (int p : part) same_window = same_window && infos[p].lo[kind] == glo && infos[p].hi[kind] == ghi;
-    if (same_window)  // every participant speculated on exactly [glo, ghi]
+    if (same_window) {  // every participant speculated on exactly [glo, ghi]
+      ks->from_spec = true;
       return parse_aligns(r, spec_all, spec_stride, spec_off, spec_handles, kind, infos, part, ks);
+    }
     const u64 n_common = span < window ? span : window;
     CKT(tml_win_select_dense(r.c, kind, ghi - n_common + 1, n_common, r.s, &a));
   } else {
@@ -399,8 +402,13 @@ int reduce_pass(Run& r, u32 kind, u32 mask, u32 mode, KindState* ks, int series_
   return TML_OK;
 }
 
-int bands(Run& r, tml_kind_result* res) {
+// `extra` (n_extra doubles per rank, may be 0) rides in the band exchange: the deferred
+// reference-order sums of K3e, so that they cost no exchange of their own.  *extra_done tells the
+// caller whether the exchange happened (no aligned window -> no band exchange).
+int bands(Run& r, tml_kind_result* res, const double* extra = nullptr, int n_extra = 0,
+          double* extra_all = nullptr, bool* extra_done = nullptr) {
   const u64 n = res->n_common;
+  if (extra_done) *extra_done = false;
   if (n == 0 || !res->series) return TML_OK;
   tml_band_args a;
   memset(&a, 0, sizeof(a));
@@ -412,26 +420,32 @@ int bands(Run& r, tml_kind_result* res) {
   a.tail_first[1] = n - (n < 1000 ? n : 1000);
   tml_band_out bo;
   CKT(tml_win_bands(r.c, res->series, &a, r.s, &bo));
-  double vec[128];
+  double vec[128 + 16];
   for (int s = 0; s < 16; ++s)
     for (int b = 0; b < 3; ++b) { vec[s * 3 + b] = bo.sum[s][b]; vec[48 + s * 3 + b] = (double)bo.cnt[s][b]; }
   for (int s = 0; s < 16; ++s) { vec[96 + s] = bo.tail_first[s]; vec[112 + s] = bo.tail_last[s]; }
-  std::vector<double> all((size_t)r.world * 128);
-  CKT(r.xchg(vec, 128, all.data()));
+  const int BL = 128 + (n_extra > 0 && n_extra <= 16 ? n_extra : 0);
+  for (int q = 128; q < BL; ++q) vec[q] = extra[q - 128];
+  std::vector<double> all((size_t)r.world * BL);
+  CKT(r.xchg(vec, BL, all.data()));
+  if (BL > 128 && extra_all) {
+    for (int p = 0; p < r.world; ++p) memcpy(extra_all + (size_t)p * n_extra, all.data() + (size_t)p * BL + 128, n_extra * sizeof(double));
+    if (extra_done) *extra_done = true;
+  }
   for (int s = 0; s < 16; ++s) {
     for (int b = 0; b < 3; ++b) {
       double acc = 0.0;  // rank order, like reduce.py's sum()
       u64 cnt = 0;
       for (int p = 0; p < r.world; ++p) {
-        acc += all[(size_t)p * 128 + s * 3 + b];
-        cnt += (u64)llround(all[(size_t)p * 128 + 48 + s * 3 + b]);
+        acc += all[(size_t)p * BL + s * 3 + b];
+        cnt += (u64)llround(all[(size_t)p * BL + 48 + s * 3 + b]);
       }
       res->band_sum[s][b] = acc;
       res->band_cnt[s][b] = cnt;
     }
     double tf = NAN, tl = NAN;
-    for (int p = 0; p < r.world && std::isnan(tf); ++p) tf = all[(size_t)p * 128 + 96 + s];
-    for (int p = 0; p < r.world && std::isnan(tl); ++p) tl = all[(size_t)p * 128 + 112 + s];
+    for (int p = 0; p < r.world && std::isnan(tf); ++p) tf = all[(size_t)p * BL + 96 + s];
+    for (int p = 0; p < r.world && std::isnan(tl); ++p) tl = all[(size_t)p * BL + 112 + s];
     res->tail_first[s] = tf;
     res->tail_last[s] = tl;
   }
@@ -475,7 +489,13 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
     CKT(tml_proc_reduce_launch(c, args->proc_rows, r.w->side));
   }
   tml_win_info info;
-  CKT(tml_win_prepare(c, window, r.s, &info));
+  // R > 1: K3e (reference-order sums) runs beside the exchanges and K4; its result is collected
+  // in stage 5 and rides in the band exchange
+  const bool deferred = world > 1;
+  tml_win_set_defer(c, deferred ? 1 : 0);
+  const int prc = tml_win_prepare(c, window, r.s, &info);
+  tml_win_set_defer(c, 0);
+  CKT(prc);
   tml_proc_agg pagg;
   memset(&pagg, 0, sizeof(pagg));
   if (args->proc_rows) CKT(tml_proc_reduce_collect(c, &pagg));
@@ -567,8 +587,11 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
   }
   const double t3 = now_ms();
 
-  // ---- stage 5: trend bands
-  CKT(bands(r, &out->time));
+  // ---- stage 5: trend bands (+ the deferred reference-order sums of every rank)
+  double exact_mine[7] = {0}, exact_all[TML_MAX_RANKS * 7];
+  bool exact_done = false;
+  if (deferred) CKT(tml_win_exact_collect(c, r.s, exact_mine));
+  CKT(bands(r, &out->time, deferred ? exact_mine : nullptr, deferred ? 7 : 0, exact_all, &exact_done));
   if (same) {
     memcpy(out->mem.band_sum, out->time.band_sum, sizeof(out->time.band_sum));
     memcpy(out->mem.band_cnt, out->time.band_cnt, sizeof(out->time.band_cnt));
@@ -577,6 +600,23 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
     out->mem.has_bands = out->time.has_bands;
   } else {
     CKT(bands(r, &out->mem));
+  }
+  if (deferred) {
+    if (!exact_done) CKT(r.xchg(exact_mine, 7, exact_all));  // no aligned window: no band exchange to ride in
+    for (int p = 0; p < world; ++p) memcpy(out->infos[p].t_sums, exact_all + (size_t)p * 7, 7 * sizeof(double));
+    // lock step: the aligned window IS each rank's window, so its sums are the window sums with
+    // avg_step_cpu := traced (alignment.py:72); otherwise tml_win_select* computed exact aligned sums
+    tml_kind_result* both[2] = {&out->time, merged ? &out->mem : nullptr};
+    if (kt.from_spec) {
+      for (tml_kind_result* res : both) {
+        if (!res) continue;
+        for (u32 i = 0; i < res->n_used; ++i) {
+          const double* e = exact_all + (size_t)res->used[i] * 7;
+          memcpy(res->t_sums[i], e, 7 * sizeof(double));
+          res->t_sums[i][4] = e[5];
+        }
+      }
+    }
   }
   const double t4 = now_ms();
   out->n_exchanges = r.n_exchanges;
