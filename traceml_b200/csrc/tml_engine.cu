@@ -1249,7 +1249,9 @@ static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaSt
   if (n <= 0) { CK(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), s)); return TML_OK; }
   const long long nchunks = (n + XS_CHUNK - 1) / XS_CHUNK, ngroups = (nchunks + XS_GROUP - 1) / XS_GROUP;
   const int planned = n > 1024 ? 1 : 0;  // tiny windows: the walk adds / composes every tile itself
-  const int max_grid = c->n_sms * 4 < 1024 ? c->n_sms * 4 : 1024;
+  // one trip of 8 chunks per CTA: the chunks that cross a binade (slow path of X3) cluster at the
+  // head of the sum and must not queue up behind each other inside one CTA
+  const long long max_grid = (long long)c->n_sms * 8;
   if ((u64)nchunks > c->cap_xs || !c->d_xs_buf) {
     cudaFree(c->d_xs_buf);
     c->d_xs_buf = nullptr; c->cap_xs = 0;
@@ -1257,7 +1259,8 @@ static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaSt
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_csum = take(cap * 8 * sizeof(double)), o_cpre = take(cap * 8 * sizeof(double));
-    const size_t o_btot = take(1024 * 8 * sizeof(double)), o_bpre = take(1024 * 8 * sizeof(double));
+    const size_t nb_cap = (size_t)((cap + XS_WARPS - 1) / XS_WARPS + 1);
+    const size_t o_btot = take(nb_cap * 8 * sizeof(double)), o_bpre = take(nb_cap * 8 * sizeof(double));
     const size_t o_plan = take(cap * 8 * sizeof(int)), o_ea = take(cap * 8 * sizeof(int));
     const size_t o_fn = take(cap * 7 * sizeof(XsFn)), o_gfn = take(gcap * 7 * sizeof(XsFn));
     const size_t o_gplan = take(gcap * 8 * sizeof(int)), o_tiles = take((size_t)XS_SLOT_CAP * sizeof(XsTileMaps));
@@ -1281,13 +1284,17 @@ static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaSt
     CK(cudaPeekAtLastError());
     k_xs_bscan<<<1, 1024, 0, s>>>(w, grid);
     CK(cudaPeekAtLastError());
-    k_xs_compose<<<grid, XS_WARPS * 32, 0, s>>>(src, n, nchunks, w);
+    {
+      long long per = (nchunks + grid - 1) / grid;  // X1's run length (xs_block_range)
+      per = (per + XS_WARPS - 1) / XS_WARPS * XS_WARPS;
+      k_xs_compose<<<(int)((nchunks + XS_CW - 1) / XS_CW), XS_CW * 32, 0, s>>>(src, n, nchunks, w, (int)per);
+    }
     CK(cudaPeekAtLastError());
     k_xs_groups<<<(int)((ngroups * 7 + 7) / 8), 256, 0, s>>>(w, nchunks, ngroups);
     CK(cudaPeekAtLastError());
     c->launches += 4;
   }
-  k_xs_walk<<<1, 7 * 32, 0, s>>>(src, n, nchunks, ngroups, w, planned, d_out, c->d_xs_stats);
+  k_xs_walk<<<7, 256, 0, s>>>(src, n, nchunks, ngroups, w, planned, d_out, c->d_xs_stats);
   CK(cudaPeekAtLastError());
   c->launches += 1;
   return TML_OK;

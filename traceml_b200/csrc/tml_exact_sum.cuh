@@ -40,7 +40,9 @@ struct XsSrc {
 
 struct XsTileMaps {  // one unsafe (chunk, chain): tile maps under exponent ea (h = 0) and ea + 1 (h = 1)
   XsFn f[2][XS_TILES];
+  double x[XS_CHUNK];  // and the chain's addends, in summation order: the crossing tile is added from here
 };
+struct XsTileHead { XsFn f[2][XS_TILES]; };  // the part of a slot the walk stages in shared memory
 
 struct XsWork {  // device workspace of one launch
   double* csum;   // [nchunks][8] approximate chunk sums
@@ -83,6 +85,13 @@ __device__ __forceinline__ void xs_addends(const tml_window_row* __restrict__ ro
   o[4] = s.aligned ? fmax(0.0, traced) : wall;
   o[5] = traced;
   o[6] = dl + traced;
+}
+
+__device__ __forceinline__ double xs_pick(const double (&o)[7], int k) {
+  double x = o[0];
+#pragma unroll
+  for (int m = 1; m < 7; ++m) x = (k == m) ? o[m] : x;
+  return x;
 }
 
 __device__ __forceinline__ u64 shfl_down_u64(u64 v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -164,124 +173,156 @@ __global__ void __launch_bounds__(XS_WARPS * 32) k_xs_partial(const XsSrc s, lon
   if (threadIdx.x < 7) w.btot[(long long)blockIdx.x * 8 + threadIdx.x] = run;
 }
 
-// ---- X2: exclusive scan of the CTA totals, nblocks <= 1024
+// ---- X2: exclusive scan of the CTA totals (one CTA, tiles of 1024 with a running carry)
 __global__ void __launch_bounds__(1024) k_xs_bscan(XsWork w, int nblocks) {
   __shared__ double s_warp[32][7];
+  __shared__ double s_carry[7];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  double v[7], excl[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    v[k] = (t < nblocks) ? w.btot[(long long)t * 8 + k] : 0.0;
-    double incl = v[k];
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      double y = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += y;
-    }
-    if (lane == 31) s_warp[warp][k] = incl;
-    excl[k] = incl - v[k];
-  }
+  if (t < 7) s_carry[t] = 0.0;
   __syncthreads();
-  if (warp == 0) {
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + t;
+    double v[7], excl[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-      double x = s_warp[lane][k], incl = x;
+      v[k] = (i < nblocks) ? w.btot[(long long)i * 8 + k] : 0.0;
+      double incl = v[k];
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         double y = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += y;
       }
-      s_warp[lane][k] = incl - x;
+      if (lane == 31) s_warp[warp][k] = incl;
+      excl[k] = incl - v[k];
     }
-  }
-  __syncthreads();
-  if (t < nblocks) {
+    __syncthreads();
+    if (warp == 0) {
 #pragma unroll
-    for (int k = 0; k < 7; ++k) w.bpre[(long long)t * 8 + k] = s_warp[warp][k] + excl[k];
+      for (int k = 0; k < 7; ++k) {
+        double x = s_warp[lane][k], incl = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          double y = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += y;
+        }
+        s_warp[lane][k] = incl - x;
+      }
+    }
+    __syncthreads();
+    double tot[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const double pre = s_carry[k] + s_warp[warp][k] + excl[k];
+      if (i < nblocks) w.bpre[(long long)i * 8 + k] = pre;
+      tot[k] = pre + v[k];
+    }
+    __syncthreads();
+    if (t == 1023) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s_carry[k] = tot[k];
+    }
+    __syncthreads();
   }
   if (t == 0) *w.nslots = 0u;
 }
 
-// ---- X3
-__global__ void __launch_bounds__(XS_WARPS * 32) k_xs_compose(const XsSrc s, long long n, long long nchunks, XsWork w) {
+// ---- X3.  One warp per chunk.  Phase A: lane = row (8 passes of 32 rows, every load of a pass in
+// flight at once); the seven addends of a row are derived ONCE and parked in shared memory, chain
+// by chain.  Phase B: lane = (g, k), row quarter g = lane >> 3 (64 consecutive rows), chain
+// k = lane & 7 (k == 7 idles): a lane walks its 64 rows serially for ITS chain -- one LDS, one
+// branch-free FPU element map, one branch-free compose per row -- and the four quarters of a chain
+// are joined by two shuffle levels.  ncu history (W = 4e6, 28 M element maps): v1 lane = 8 rows x 7
+// chains from global memory, 95 M warp instructions, 217 us; v3 lane = (g, k) deriving all seven
+// addends per lane, 209 M, 197 us; this version: see profiles/.
+#define XS_CW 2                    // warps (chunks in flight) per compose CTA
+#define XS_SG 65                   // doubles per row quarter (64 + 1: quarters in different banks)
+#define XS_SK (4 * XS_SG + 8)      // doubles per chain
+
+__global__ void __launch_bounds__(XS_CW * 32) k_xs_compose(const XsSrc s, long long n, long long nchunks, XsWork w,
+                                                          int chunks_per_block) {
+  __shared__ double s_x[XS_CW][7 * XS_SK];
   const tml_window_row* rows = xs_rows(s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long c_lo, c_hi;
-  xs_block_range(nchunks, &c_lo, &c_hi);
-  for (long long ch = c_lo + warp; ch < c_hi; ch += XS_WARPS) {
-    int e[7];
-    double lo[7];
-    bool any_unsafe = false;
+  const int g = lane >> 3, k = lane & 7;
+  const bool live = k < 7;
+  double* sm = s_x[warp];
+  // this CTA serves the chunks [blockIdx.x * XS_CW, +XS_CW); the prefix tables are indexed by the
+  // CTA that PRODUCED them in X1 (runs of `chunks_per_block` chunks)
+  const long long ch = (long long)blockIdx.x * XS_CW + warp;
+  if (ch >= nchunks) return;
+  const long long owner = ch / chunks_per_block;
+  double lo = 0.0;
+  int e = XS_PLAN_ZERO;
+  if (live) {
+    lo = w.bpre[owner * 8 + k] + w.cpre[ch * 8 + k];
+    e = xs_plan(lo, lo + w.csum[ch * 8 + k]);
+  }
+  // ---- phase A
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      lo[k] = w.bpre[(long long)blockIdx.x * 8 + k] + w.cpre[ch * 8 + k];
-      e[k] = xs_plan(lo[k], lo[k] + w.csum[ch * 8 + k]);
-      any_unsafe = any_unsafe || (e[k] == XS_PLAN_UNSAFE && lo[k] > 0.0);
-    }
-    XsFn f[7];
-    unsigned bad = 0u;  // bit k: some element of chain k does not fit under the planned exponent
+  for (int it = 0; it < XS_CHUNK / 32; ++it) {
+    const int r = it * 32 + lane;
+    double o[7];
+    xs_addends(rows, s, ch * XS_CHUNK + r, n, o);
+    double* dst = sm + (r >> 6) * XS_SG + (r & 63);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) f[k] = xs_identity();
-    const long long p0 = ch * XS_CHUNK + lane * XS_ROWS_PER_LANE;
+    for (int m = 0; m < 7; ++m) dst[m * XS_SK] = o[m];
+  }
+  __syncwarp();
+  // ---- phase B
+  const double* mine = sm + (live ? k : 0) * XS_SK + g * XS_SG;
+  double scale = e >= 1 ? xs_scale(e) : 0.0;
+  if (e >= 1 && scale == 0.0) e = XS_PLAN_UNSAFE;  // exponent without a normal scale (sums < 2^-971): walk adds rows
+  XsFn f = xs_identity();
+  bool bad = false;
+  if (e >= 1) {
+#pragma unroll 8
+    for (int j = 0; j < 64; ++j) f = xs_compose_nb(f, xs_elem_fp_nb(mine[j], scale, &bad));
+  }
+  // join the four quarters of each chain: lanes k, k + 8, k + 16, k + 24 (in row order)
 #pragma unroll
-    for (int j = 0; j < XS_ROWS_PER_LANE; ++j) {
-      double o[7];
-      xs_addends(rows, s, p0 + j, n, o);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        if (e[k] >= 1) {
-          XsFn g;
-          if (!xs_elem_raw(o[k], e[k], &g)) bad |= 1u << k;
-          f[k] = xs_compose_raw(f[k], g);
-        }
-      }
-    }
-    bad = __reduce_or_sync(0xffffffffu, bad);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      XsFn r = xs_seal(xs_warp_compose_raw(f[k], lane), ((bad >> k) & 1u) == 0u);  // 256 maps < 2^53: < 2^61
-      if (e[k] == XS_PLAN_ZERO) r = xs_identity();
-      else if (e[k] < 1) r = xs_invalid();
-      if (lane == 0) w.fn[ch * 7 + k] = r;
-    }
-    // a chunk whose running sum changes binade: tile maps under both candidate exponents, so the
-    // walk redoes only the ONE tile that holds the crossing (rare: ~ one chunk per binade and chain)
-    if (any_unsafe) {
-      for (int k = 0; k < 7; ++k) {
-        if (!(e[k] == XS_PLAN_UNSAFE && lo[k] > 0.0)) continue;
-        const int ea = xs_exp(lo[k] * (1.0 - 1.0e-6));
-        unsigned int slot = 0;
-        if (lane == 0) slot = atomicAdd(w.nslots, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= XS_SLOT_CAP || ea < 1 || ea >= 0x7fd) continue;  // plain UNSAFE: the walk adds row by row
+  for (int d = 8; d <= 16; d <<= 1) {
+    XsFn m;
+    m.c0 = shfl_down_u64(f.c0, d);
+    m.c1 = shfl_down_u64(f.c1, d);
+    const bool mbad = __shfl_down_sync(0xffffffffu, bad ? 1 : 0, d) != 0;
+    if ((g & ((2 * d / 8) - 1)) == 0) { f = xs_compose_nb(f, m); bad = bad || mbad; }
+  }
+  if (live && g == 0) {
+    XsFn r = xs_seal(f, !bad);  // 256 maps < 2^53 each: the raw sums stay < 2^61
+    if (e == XS_PLAN_ZERO) r = xs_identity();
+    else if (e < 1) r = xs_invalid();
+    w.fn[ch * 7 + k] = r;
+  }
+  // a chunk whose running sum changes binade: the eight TILE maps under both candidate exponents +
+  // the chain's addends, so the walk redoes only the one tile that holds the crossing (rare: about
+  // one chunk per binade and chain)
+  const bool unsafe = live && e == XS_PLAN_UNSAFE && lo > 0.0;
+  int plan_out = e;
+  if (__any_sync(0xffffffffu, unsafe)) {
+    const int ea = unsafe ? xs_exp(lo * (1.0 - 1.0e-6)) : 0;
+    const double sa = xs_scale(ea), sb = xs_scale(ea + 1);
+    unsigned int slot = 0xffffffffu;
+    if (unsafe && g == 0 && ea >= 1 && ea < 0x7fd && sa != 0.0 && sb != 0.0) slot = atomicAdd(w.nslots, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, k);  // from the chain's g == 0 lane
+    if (unsafe && slot < XS_SLOT_CAP) {
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
         XsFn fa = xs_identity(), fb = xs_identity();
-        for (int j = 0; j < XS_ROWS_PER_LANE; ++j) {
-          double o[7];
-          xs_addends(rows, s, p0 + j, n, o);
-          double x = o[0];
-#pragma unroll
-          for (int m = 1; m < 7; ++m) x = (k == m) ? o[m] : x;
-          fa = xs_compose(fa, xs_elem(x, ea));
-          fb = xs_compose(fb, xs_elem(x, ea + 1));
+        bool bada = false, badb = false;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const double x = mine[half * 32 + j];
+          fa = xs_compose_nb(fa, xs_elem_fp_nb(x, sa, &bada));
+          fb = xs_compose_nb(fb, xs_elem_fp_nb(x, sb, &badb));
+          w.tiles[slot].x[g * 64 + half * 32 + j] = x;
         }
-        XsFn ta, tb;
-        xs_warp_compose(fa, lane, &ta);
-        xs_warp_compose(fb, lane, &tb);
-        if ((lane & 3) == 0) {
-          w.tiles[slot].f[0][lane >> 2] = ta;
-          w.tiles[slot].f[1][lane >> 2] = tb;
-        }
-        e[k] = XS_PLAN_SLOT0 - (int)slot;
-        if (lane == 0) w.ea[ch * 8 + k] = ea;
+        w.tiles[slot].f[0][g * 2 + half] = xs_seal(fa, !bada);
+        w.tiles[slot].f[1][g * 2 + half] = xs_seal(fb, !badb);
       }
-    }
-    if (lane < 7) {
-      int ek = e[0];
-#pragma unroll
-      for (int m = 1; m < 7; ++m) ek = (lane == m) ? e[m] : ek;
-      w.plan[ch * 8 + lane] = ek;
+      if (g == 0) { plan_out = XS_PLAN_SLOT0 - (int)slot; w.ea[ch * 8 + k] = ea; }
     }
   }
+  if (live && g == 0) w.plan[ch * 8 + k] = plan_out;
 }
 
 // ---- X3b: one warp per (group, chain)
@@ -309,118 +350,203 @@ __global__ void __launch_bounds__(256) k_xs_groups(XsWork w, long long nchunks, 
   }
 }
 
-// ---- X4: warp k walks chain k.  Every lane carries the same running sum (the updates are
-// deterministic functions of broadcast values), so nothing has to be re-broadcast.
-__device__ __forceinline__ void xs_seq_tile(const tml_window_row* rows, const XsSrc& s, long long p0, long long n,
-                                            int k, int lane, double* sum) {
-  double o[7];
-  xs_addends(rows, s, p0 + lane, n, o);
-  double x = o[0];
-#pragma unroll
-  for (int m = 1; m < 7; ++m) x = (k == m) ? o[m] : x;
-  double acc = *sum;
+// ---- X4: CTA k walks chain k.  The walk itself is one warp applying integer maps (every lane
+// carries the same running sum: the updates are deterministic functions of broadcast values);
+// the other warps only help to stage what it will need into shared memory -- all group maps of a
+// batch, the chunk maps of the groups that cannot be applied whole, the tile maps of the chunks
+// that cross a binade -- so that the dependent chain never waits on global memory except for the
+// ~one 32-row tile per binade that is added row by row.
+#define XS_GB 1024   // groups staged per batch
+#define XS_IG 24     // groups of a batch whose chunk maps are staged (more: fetched on demand)
+#define XS_TS 32     // crossing chunks of a batch whose tile maps are staged (more: on demand)
+
+// Running sum of the walk as integers: s = S * 2^(eb - 1075); eb == 0 while s is still zero.
+struct XsState { int eb; u64 S; };
+
+__device__ __forceinline__ void xs_seq32(XsState* st, double x, u64* slow_rows) {
+  double acc = st->eb ? xs_pack(st->eb, st->S) : 0.0;
 #pragma unroll 8
   for (int r = 0; r < 32; ++r) acc += __shfl_sync(0xffffffffu, x, r);  // rows past n are +0.0
-  *sum = acc;
+  xs_unpack(acc, &st->eb, &st->S);
+  if (acc == 0.0) st->eb = 0;
+  *slow_rows += 32;
 }
 
-__global__ void __launch_bounds__(7 * 32) k_xs_walk(const XsSrc s, long long n, long long nchunks, long long ngroups,
-                                                    XsWork w, int planned, double* __restrict__ out,
-                                                    unsigned long long* __restrict__ stats /* [7]: rows added one by one */) {
-  __shared__ XsFn s_g[7][32];
-  __shared__ int s_ge[7][32];
-  __shared__ XsFn s_c[7][32];
-  __shared__ int s_ce[7][32];
-  __shared__ XsTileMaps s_t[7];
+// apply entries [j, end) for as long as they apply; returns the first index that did not
+__device__ __forceinline__ int xs_apply_run(XsState* st, const XsFn* __restrict__ f, const int* __restrict__ e,
+                                            int j, int end) {
+  const int eb = st->eb;
+  u64 S = st->S;
+#pragma unroll 4
+  for (; j < end; ++j) {
+    const int E = e[j];
+    if (E == XS_PLAN_ZERO) continue;
+    if (E != eb || E < 1) break;
+    const XsFn m = f[j];
+    const u64 S2 = S + ((S & 1ull) ? m.c1 : m.c0);
+    if (m.c0 == ~0ull || (S2 >> 53)) break;
+    S = S2;
+  }
+  st->S = S;
+  return j;
+}
+
+// one crossing chunk: tile maps `tm` (exponents ea, ea + 1) staged in shared memory, the chain's
+// addends in the slot (global): only the tile that crosses is fetched and added row by row
+__device__ __forceinline__ void xs_walk_tiles(const double* __restrict__ xraw, long long p0, long long n, int lane,
+                                              const XsTileHead* tm, int ea, XsState* st, u64* slow_rows) {
+#pragma unroll 1
+  for (int t = 0; t < XS_TILES; ++t) {
+    if (p0 + t * 32 >= n) break;
+    const int h = st->eb - ea;
+    if ((h == 0 || h == 1) && xs_apply_s(st->eb, &st->S, tm->f[h][t], st->eb)) continue;
+    xs_seq32(st, xraw[t * 32 + lane], slow_rows);
+  }
+}
+
+// a chunk without maps (start-up from 0, or the slot table was full)
+__device__ __forceinline__ void xs_walk_rows(const tml_window_row* rows, const XsSrc& s, long long p0, long long n,
+                                             int k, int lane, XsState* st, u64* slow_rows) {
+  double x[XS_TILES];
+#pragma unroll
+  for (int t = 0; t < XS_TILES; ++t) {
+    double o[7];
+    xs_addends(rows, s, p0 + t * 32 + lane, n, o);
+    x[t] = xs_pick(o, k);
+  }
+#pragma unroll
+  for (int t = 0; t < XS_TILES; ++t) {
+    if (p0 + t * 32 < n) {
+      bool done = false;
+      if (st->eb >= 1 && st->eb < 0x7ff && p0 > 0) {  // compose this tile under the true exponent
+        XsFn f = xs_warp_compose(xs_elem(x[t], st->eb), lane);
+        f.c0 = __shfl_sync(0xffffffffu, f.c0, 0); f.c1 = __shfl_sync(0xffffffffu, f.c1, 0);
+        done = xs_apply_s(st->eb, &st->S, f, st->eb);
+      }
+      if (!done) xs_seq32(st, x[t], slow_rows);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) k_xs_walk(const XsSrc s, long long n, long long nchunks, long long ngroups,
+                                                 XsWork w, int planned, double* __restrict__ out,
+                                                 unsigned long long* __restrict__ stats /* [7]: rows added one by one */) {
+  __shared__ XsFn s_g[XS_GB];
+  __shared__ int s_ge[XS_GB];
+  __shared__ int s_inv[XS_IG];
+  __shared__ int s_ninv;
+  __shared__ XsFn s_c[XS_IG + 1][XS_GROUP];      // row XS_IG: on-demand spare
+  __shared__ int s_ce[XS_IG + 1][XS_GROUP];
+  __shared__ short s_ts[XS_IG + 1][XS_GROUP];    // staged tile-map index of a crossing chunk, or -1
+  __shared__ XsTileHead s_t[XS_TS + 1];          // entry XS_TS: on-demand spare
+  __shared__ int s_tea[XS_TS + 1];
+  __shared__ int s_tslot[XS_TS];                 // global slot of staged entry
+  __shared__ int s_nts;
   const tml_window_row* rows = xs_rows(s);
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double sum = 0.0;
-  unsigned long long slow_rows = 0;
-  for (long long gb = 0; gb < ngroups; gb += 32) {
-    {
+  const int k = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  XsState st;
+  st.eb = 0; st.S = 0ull;
+  u64 slow_rows = 0;
+  for (long long gb = 0; gb < ngroups; gb += XS_GB) {
+    const int cnt = (int)((ngroups - gb) < XS_GB ? (ngroups - gb) : XS_GB);
+    __syncthreads();
+    // ---- stage 1: every group map of the batch
+    for (int i = tid; i < cnt; i += blockDim.x) {
       XsFn gf = xs_invalid();
       int ge = XS_PLAN_UNSAFE;
-      if (planned && gb + lane < ngroups) { gf = w.gfn[(gb + lane) * 7 + k]; ge = w.gplan[(gb + lane) * 8 + k]; }
-      s_g[k][lane] = gf; s_ge[k][lane] = ge;
+      if (planned) { gf = w.gfn[(gb + i) * 7 + k]; ge = w.gplan[(gb + i) * 8 + k]; }
+      s_g[i] = gf; s_ge[i] = ge;
     }
-    __syncwarp();
-    const int gcount = (int)((ngroups - gb) < 32 ? (ngroups - gb) : 32);
-    for (int j = 0; j < gcount; ++j) {
-      const int E = s_ge[k][j];
-      if (E == XS_PLAN_ZERO) continue;
-      if (E >= 1 && xs_apply(&sum, s_g[k][j], E)) continue;
-      // ---- the group, chunk by chunk
-      const long long c0 = (gb + j) * XS_GROUP;
-      __syncwarp();
-      {
-        XsFn cf = xs_invalid();
-        int ce = XS_PLAN_UNSAFE;
-        if (planned && c0 + lane < nchunks) { cf = w.fn[(c0 + lane) * 7 + k]; ce = w.plan[(c0 + lane) * 8 + k]; }
-        s_c[k][lane] = cf; s_ce[k][lane] = ce;
+    __syncthreads();
+    // ---- stage 2: which groups must be walked chunk by chunk (in order)
+    if (warp == 0) {
+      int ninv = 0;
+      for (int base = 0; base < cnt; base += 32) {
+        const bool bad = (base + lane < cnt) && s_ge[base + lane] == XS_PLAN_UNSAFE;
+        const unsigned m = __ballot_sync(0xffffffffu, bad);
+        const int pos = ninv + __popc(m & ((1u << lane) - 1u));
+        if (bad && pos < XS_IG) s_inv[pos] = base + lane;
+        ninv += __popc(m);
       }
-      __syncwarp();
-      const int ccount = (int)((nchunks - c0) < XS_GROUP ? (nchunks - c0) : XS_GROUP);
-      for (int q = 0; q < ccount; ++q) {
-        const int CE = s_ce[k][q];
-        if (CE == XS_PLAN_ZERO) continue;
-        if (CE >= 1 && xs_apply(&sum, s_c[k][q], CE)) continue;
-        const long long p0 = (c0 + q) * XS_CHUNK;
-        if (CE <= XS_PLAN_SLOT0) {
-          // ---- tile maps under ea / ea + 1; the tile that crosses is added row by row
-          const int slot = XS_PLAN_SLOT0 - CE;
-          // one round trip: candidate exponent, tile maps and this chain's addends of all 8 tiles
-          const int ea = w.ea[(c0 + q) * 8 + k];
-          XsFn tm = xs_invalid();
-          if (lane < 2 * XS_TILES) tm = (&w.tiles[slot].f[0][0])[lane];
-          double x[XS_TILES];
-#pragma unroll
-          for (int t = 0; t < XS_TILES; ++t) {
-            double o[7];
-            xs_addends(rows, s, p0 + t * 32 + lane, n, o);
-            x[t] = o[0];
-#pragma unroll
-            for (int m = 1; m < 7; ++m) x[t] = (k == m) ? o[m] : x[t];
-          }
+      if (lane == 0) s_ninv = ninv < XS_IG ? ninv : XS_IG;
+    }
+    __syncthreads();
+    const int ninv = s_ninv;
+    for (int i = tid; i < ninv * XS_GROUP; i += blockDim.x) {
+      const int gi = i / XS_GROUP, q = i % XS_GROUP;
+      const long long ch = (gb + s_inv[gi]) * XS_GROUP + q;
+      XsFn cf = xs_invalid();
+      int ce = XS_PLAN_ZERO;  // past the end: nothing to add
+      if (ch < nchunks) { ce = XS_PLAN_UNSAFE; if (planned) { cf = w.fn[ch * 7 + k]; ce = w.plan[ch * 8 + k]; } }
+      s_c[gi][q] = cf; s_ce[gi][q] = ce; s_ts[gi][q] = -1;
+    }
+    __syncthreads();
+    // ---- stage 3: tile maps of the crossing chunks among them
+    if (warp == 0) {
+      int nts = 0;
+      for (int gi = 0; gi < ninv; ++gi) {
+        const int ce = s_ce[gi][lane];
+        const bool has = ce <= XS_PLAN_SLOT0;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        const int pos = nts + __popc(m & ((1u << lane) - 1u));
+        if (has && pos < XS_TS) { s_ts[gi][lane] = (short)pos; s_tslot[pos] = XS_PLAN_SLOT0 - ce; }
+        nts += __popc(m);
+      }
+      if (lane == 0) s_nts = nts < XS_TS ? nts : XS_TS;
+    }
+    __syncthreads();
+    const int nts = s_nts;
+    for (int i = tid; i < nts * 2 * XS_TILES; i += blockDim.x) {
+      const int ti = i / (2 * XS_TILES), e = i % (2 * XS_TILES);
+      (&s_t[ti].f[0][0])[e] = (&w.tiles[s_tslot[ti]].f[0][0])[e];
+    }
+    for (int gi = tid / XS_GROUP; gi < ninv; gi += blockDim.x / XS_GROUP) {
+      const int q = tid % XS_GROUP;
+      const int ti = s_ts[gi][q];
+      if (ti >= 0) s_tea[ti] = w.ea[((gb + s_inv[gi]) * XS_GROUP + q) * 8 + k];
+    }
+    __syncthreads();
+    // ---- stage 4: the walk (warp 0)
+    if (warp == 0) {
+      int next_inv = 0;
+      for (int j = 0; j < cnt; ++j) {
+        j = xs_apply_run(&st, s_g, s_ge, j, cnt);
+        if (j >= cnt) break;
+        const long long c0 = (gb + j) * XS_GROUP;
+        int gi = XS_IG;  // spare row
+        if (next_inv < ninv && s_inv[next_inv] == j) {
+          gi = next_inv++;
+        } else {  // not staged (list overflow, or a planned map that did not apply): fetch now
           __syncwarp();
-          if (lane < 2 * XS_TILES) (&s_t[k].f[0][0])[lane] = tm;
+          const long long ch = c0 + lane;
+          XsFn cf = xs_invalid();
+          int ce = XS_PLAN_ZERO;
+          if (ch < nchunks) { ce = XS_PLAN_UNSAFE; if (planned) { cf = w.fn[ch * 7 + k]; ce = w.plan[ch * 8 + k]; } }
+          s_c[gi][lane] = cf; s_ce[gi][lane] = ce; s_ts[gi][lane] = -1;
           __syncwarp();
-#pragma unroll
-          for (int t = 0; t < XS_TILES; ++t) {
-            if (p0 + t * 32 < n) {
-              const int eb = xs_exp(sum);
-              const int h = eb - ea;
-              if (!((h == 0 || h == 1) && xs_apply(&sum, s_t[k].f[h][t], eb))) {
-                double acc = sum;
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) acc += __shfl_sync(0xffffffffu, x[t], r);
-                sum = acc;
-                slow_rows += 32;
-              }
+        }
+        for (int q = 0; q < XS_GROUP; ++q) {
+          q = xs_apply_run(&st, s_c[gi], s_ce[gi], q, XS_GROUP);
+          if (q >= XS_GROUP) break;
+          const int CE = s_ce[gi][q];
+          const long long p0 = (c0 + q) * XS_CHUNK;
+          if (p0 >= n) break;
+          if (CE <= XS_PLAN_SLOT0) {
+            int ti = s_ts[gi][q];
+            if (ti < 0) {  // tile maps not staged: fetch now
+              ti = XS_TS;
+              __syncwarp();
+              if (lane < 2 * XS_TILES) (&s_t[ti].f[0][0])[lane] = (&w.tiles[XS_PLAN_SLOT0 - CE].f[0][0])[lane];
+              if (lane == 0) s_tea[ti] = w.ea[(c0 + q) * 8 + k];
+              __syncwarp();
             }
+            xs_walk_tiles(w.tiles[XS_PLAN_SLOT0 - CE].x, p0, n, lane, &s_t[ti], s_tea[ti], &st, &slow_rows);
+          } else {
+            xs_walk_rows(rows, s, p0, n, k, lane, &st, &slow_rows);
           }
-          continue;
-        }
-        // ---- no maps (start-up from 0, or the slot table is full): every row is a real add
-#pragma unroll 1
-        for (int t = 0; t < XS_TILES; ++t) {
-          if (p0 + t * 32 >= n) break;
-          const int eb = xs_exp(sum);
-          bool done = false;
-          if (sum > 0.0 && eb >= 1 && eb < 0x7ff && p0 > 0) {  // compose this tile under the true exponent
-            double o[7];
-            xs_addends(rows, s, p0 + t * 32 + lane, n, o);
-            double x = o[0];
-#pragma unroll
-            for (int m = 1; m < 7; ++m) x = (k == m) ? o[m] : x;
-            XsFn f = xs_warp_compose(xs_elem(x, eb), lane);
-            f.c0 = __shfl_sync(0xffffffffu, f.c0, 0); f.c1 = __shfl_sync(0xffffffffu, f.c1, 0);
-            done = xs_apply(&sum, f, eb);
-          }
-          if (!done) { xs_seq_tile(rows, s, p0 + t * 32, n, k, lane, &sum); slow_rows += 32; }
         }
       }
     }
-    __syncwarp();
   }
-  if (lane == 0) { out[k] = sum; if (stats) stats[k] = slow_rows; }
+  if (warp == 0 && lane == 0) { out[k] = st.eb ? xs_pack(st.eb, st.S) : 0.0; if (stats) stats[k] = slow_rows; }
 }

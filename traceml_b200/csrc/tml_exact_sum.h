@@ -124,6 +124,59 @@ XS_HD XsFn xs_compose_raw(const XsFn& f, const XsFn& g) {
   h.c1 = f.c1 + (((1ull + f.c1) & 1ull) ? g.c1 : g.c0);
   return h;
 }
+// The same map through the FPU (hot loops): t = x / u is an exact scaling by a power of two,
+// floor(t) and t - floor(t) are exact for t < 2^53, so q, "above / below / at one half" come out of
+// one multiply, one floor, one subtract and two compares instead of a page of 64-bit shifts.
+// ``scale`` = 2^(1075 - eb) from xs_scale (0.0: eb too small for a normal scale -> integer path).
+XS_HD double xs_scale(int eb) {
+  const int f = 2098 - eb;  // biased exponent of 2^(1075 - eb)
+  return (f >= 1 && f <= 2046) ? xs_from_bits((unsigned long long)f << 52) : 0.0;
+}
+XS_HD bool xs_elem_fp(double x, int eb, double scale, XsFn* out) {
+  if (scale == 0.0) return xs_elem_raw(x, eb, out);
+  const double t = x * scale;
+  if (!(t >= 0.0 && t < 9007199254740992.0)) { *out = xs_identity(); return false; }  // < 0, nan, >= 2^53
+#if defined(__CUDA_ARCH__)
+  const double fl = floor(t);
+#else
+  const double fl = __builtin_floor(t);
+#endif
+  const unsigned long long q = (unsigned long long)fl;
+  const double fr = t - fl;
+  const unsigned long long up = fr > 0.5 ? 1ull : 0ull;
+  const unsigned long long tie = fr == 0.5 ? 1ull : 0ull;
+  out->c0 = q + (up | (tie & q));           // tie: S + c must be even; S even -> c even
+  out->c1 = q + (up | (tie & (q + 1ull)));  //                          S odd  -> c odd
+  return true;
+}
+
+// Branch-free forms for the compose kernel's inner loop (scale != 0 guaranteed by the caller):
+// *bad accumulates "this element does not fit under the exponent" (negative, nan, >= 2^(e+1));
+// the garbage map such an element yields is discarded when the chunk map is sealed.
+XS_HD XsFn xs_elem_fp_nb(double x, double scale, bool* bad) {
+  const double t = x * scale;
+  *bad = *bad || !(t >= 0.0 && t < 9007199254740992.0);
+#if defined(__CUDA_ARCH__)
+  const double fl = floor(t);
+#else
+  const double fl = __builtin_floor(t);
+#endif
+  const unsigned long long q = (unsigned long long)fl;
+  const double fr = t - fl;
+  const unsigned long long up = fr > 0.5 ? 1ull : 0ull;
+  const unsigned long long tie = fr == 0.5 ? 1ull : 0ull;
+  XsFn f;
+  f.c0 = q + (up | (tie & q));
+  f.c1 = q + (up | (tie & (q + 1ull)));
+  return f;
+}
+XS_HD XsFn xs_compose_nb(const XsFn& f, const XsFn& g) {
+  XsFn h;
+  h.c0 = f.c0 + ((f.c0 & 1ull) ? g.c1 : g.c0);
+  h.c1 = f.c1 + ((f.c1 & 1ull) ? g.c0 : g.c1);
+  return h;
+}
+
 // close a raw composition: anything that could leave the binade (or saw an invalid element) is invalid
 XS_HD XsFn xs_seal(const XsFn& f, bool ok) {
   if (!ok || f.c0 >= (1ull << 53) || f.c1 >= (1ull << 53)) return xs_invalid();
@@ -141,6 +194,24 @@ XS_HD bool xs_apply(double* s, const XsFn& f, int eb) {
   const unsigned long long S2 = S + ((S & 1ull) ? f.c1 : f.c0);
   if (S2 >= (1ull << 53)) return false;
   *s = xs_from_bits(((unsigned long long)eb << 52) | (S2 & 0x000fffffffffffffull));
+  return true;
+}
+
+// Walk state as integers: (eb, S) with s = S * 2^(eb - 1075); eb == 0: s is zero / subnormal.
+XS_HD void xs_unpack(double s, int* eb, unsigned long long* S) {
+  const unsigned long long b = xs_bits(s);
+  *eb = (int)((b >> 52) & 0x7ffull);
+  *S = (b & 0x000fffffffffffffull) | 0x0010000000000000ull;
+  if (b >> 63) *eb = 0;  // negative: never applies
+}
+XS_HD double xs_pack(int eb, unsigned long long S) {
+  return xs_from_bits(((unsigned long long)eb << 52) | (S & 0x000fffffffffffffull));
+}
+XS_HD bool xs_apply_s(int eb, unsigned long long* S, const XsFn& f, int E) {
+  if (E != eb || E <= 0 || E >= 0x7ff || f.c0 == ~0ull) return false;
+  const unsigned long long S2 = *S + ((*S & 1ull) ? f.c1 : f.c0);
+  if (S2 >> 53) return false;
+  *S = S2;
   return true;
 }
 

@@ -26,12 +26,21 @@ extern "C" int tml_xs_host_sum(const double* x, uint64_t n, int planned, double*
     for (uint64_t c = 0; c < nchunks; ++c) {  // X3
       if (plan[c] == XS_PLAN_ZERO) { fn[c] = xs_identity(); continue; }
       if (plan[c] < 1) continue;
-      XsFn f = xs_identity();  // the kernels' hot loop: raw compose, sealed once per chunk
+      XsFn f = xs_identity();  // the kernels' hot loop: FPU element maps, raw compose, sealed once per chunk
       bool ok = true;
+      const double scale = xs_scale(plan[c]);
       const uint64_t lo = c * XS_CHUNK, hi = lo + XS_CHUNK < n ? lo + XS_CHUNK : n;
       for (uint64_t i = lo; i < hi; ++i) {
-        XsFn g;
-        ok = xs_elem_raw(x[i], plan[c], &g) && ok;
+        XsFn g, gi;
+        ok = xs_elem_fp(x[i], plan[c], scale, &g) && ok;
+        const bool oki = xs_elem_raw(x[i], plan[c], &gi);  // the integer formulation must agree, always
+        if (oki && (g.c0 != gi.c0 || g.c1 != gi.c1)) return TML_ERR_STATE;
+        if (oki && scale != 0.0) {  // and so must the branch-free forms of the compose kernel
+          bool bad = false;
+          const XsFn gn = xs_elem_fp_nb(x[i], scale, &bad);
+          const XsFn h1 = xs_compose_raw(f, g), h2 = xs_compose_nb(f, gn);
+          if (bad || gn.c0 != gi.c0 || gn.c1 != gi.c1 || h1.c0 != h2.c0 || h1.c1 != h2.c1) return TML_ERR_STATE;
+        }
         f = xs_compose_raw(f, g);
       }
       fn[c] = xs_seal(f, ok);
@@ -54,7 +63,11 @@ extern "C" int tml_xs_host_sum(const double* x, uint64_t n, int planned, double*
   uint64_t slow = 0;
   for (uint64_t g = 0; g < ngroups; ++g) {  // X4
     if (gplan[g] == XS_PLAN_ZERO) continue;
-    if (gplan[g] >= 1 && xs_apply(&s, gfn[g], gplan[g])) continue;
+    {
+      int eb; unsigned long long S;
+      xs_unpack(s, &eb, &S);
+      if (gplan[g] >= 1 && xs_apply_s(eb, &S, gfn[g], gplan[g])) { s = xs_pack(eb, S); continue; }
+    }
     const uint64_t clo = g * XS_GROUP, chi = clo + XS_GROUP < nchunks ? clo + XS_GROUP : nchunks;
     for (uint64_t c = clo; c < chi; ++c) {
       if (plan[c] == XS_PLAN_ZERO) continue;
