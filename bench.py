@@ -779,6 +779,11 @@ def main():
         "k_window_rows": {"ms": med.get("k3a"), "bytes": k3a_bytes,
                           "GBps": k3a_bytes / (med["k3a"] * 1e-3) / 1e9 if med.get("k3a") else None},
     }
+    if getattr(res["reduce"], "fused_rows", False):
+        # single rank: ring -> series in one kernel; 128 B record read + 16 series x 8 B written per step
+        fb = W * 256.0
+        kernels = {"k_window_fused": {"ms": med.get("k3a"), "bytes": fb,
+                                      "GBps": fb / (med["k3a"] * 1e-3) / 1e9 if med.get("k3a") else None}}
     if R > 1 and med.get("k4"):
         # step-sharded K4 loads (R-1)/R of its rows from peer HBM: NVLink 5 is its bound, not the
         # local HBM.  Denominator: the measured peer copy of 770 GB/s per direction per GPU

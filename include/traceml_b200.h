@@ -224,6 +224,7 @@ typedef struct tml_win_info {
  * reduce, for the per-rank summaries and the rank tie-breaks.  Off by default (stage-by-stage
  * callers get exact sums directly).                                                       */
 int tml_win_set_defer(tml_ctx* ctx, int on);
+
 int tml_win_exact_collect(tml_ctx* ctx, void* stream, double t_sums[7]);
 /* rows the last K3e walk had to add one by one, per chain (diagnostic) */
 int tml_win_exact_stats(tml_ctx* ctx, uint64_t slow_rows[7]);
@@ -251,6 +252,19 @@ typedef struct tml_align_info {
    * (step_memory/model.py:175,224-246)                                       */
   double m_sums[4];
 } tml_align_info;
+
+/* Single-rank bulk path.  With one rank the per-step median and worst ARE the rank's values
+ * (diagnostics/step_time/adapters.py:92-139 over one column), so ring -> series is one pass
+ * (k_window_fused): the 64-B WindowRows are never written or re-read.  tml_win_peek: how many
+ * records the ring retains and how many fall into the last-`window` time window (sizes the series
+ * buffer, [16][n_window] doubles).  tml_win_fused: *ok = 1 and `aligned` filled if the window is
+ * dense (every row a candidate of both kinds, consecutive step ids; memory window == time
+ * window); *ok = 0: use the staged path.  Per-rank sums are the deterministic tree sums: a single
+ * rank has no tie to break (rel <= 1e-13 of the reference-order sums).                    */
+int tml_win_peek(tml_ctx* ctx, uint32_t window, uint64_t* n_retained, uint64_t* n_window);
+int tml_win_fused(tml_ctx* ctx, uint32_t window, double* series, void* stream, tml_win_info* out,
+                  tml_align_info* aligned, uint32_t* ok);
+
 
 /* Stage 3 (local, identical on every rank given the reduced presence).
  * Prefix-scan of the common-step flags, keep the last `window`, gather this

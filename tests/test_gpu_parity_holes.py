@@ -89,6 +89,60 @@ def test_large_window_vs_numpy_oracle(cuda, scenario, R, S, W):
             e.close()
 
 
+@pytest.mark.parametrize("scenario,S,W,ring,fused", [
+    ("balanced", 300_000, 300_000, None, True), ("input_straggler", 450_000, 300_000, None, True),
+    ("balanced", 400_000, 400_000, 250_000, True),      # ring wrapped: the window is what the ring retains
+    ("duplicates", 200_000, 200_000, None, False),      # re-flushed step ids: not dense -> staged path
+    ("balanced", 100_000, 100_000, None, False),        # below the bulk threshold: reference-order sums
+])
+def test_single_rank_bulk_path(cuda, scenario, S, W, ring, fused):
+    """World of one, large window: ring -> series in one kernel (k_window_fused), accepted only if
+    the window is dense.  Against the numpy oracle where step ids are unique, and bit for bit
+    against the staged Python-sequenced path otherwise."""
+    import replay
+    from oracle import fast_oracle
+    from traceml_b200 import sections
+    from traceml_b200.engine import Engine
+
+    recs = replay.make_step_replay(scenario, 1, S, seed=77)[0]
+    slots = ring or (S + 8)
+    kept = recs[-slots:]
+
+    def run(native):
+        eng = Engine(device=0, rank=0, world=1, ring_slots=slots, proc_slots=64)
+        eng.load_steps(recs)
+        torch.cuda.synchronize()
+        try:
+            res = sections.SummaryEngine([eng], ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=1,
+                                         native=native).build(W, W)
+            red = res["reduce"]
+            ser = red.time.series.cpu().numpy().copy()
+            mser = red.mem.series.cpu().numpy().copy()
+            return res, ser, mser, bool(getattr(red, "fused_rows", False))
+        finally:
+            eng.close()
+
+    got, ser, mser, was_fused = run(True)
+    assert was_fused == fused
+    staged, ser2, mser2, _ = run(False)
+    np.testing.assert_array_equal(ser[:12], ser2[:12])
+    np.testing.assert_array_equal(mser[12:16], mser2[12:16])
+    for sec in ("step_time", "step_memory"):
+        assert_struct(plain(got[sec]), plain(staged[sec]), f"fused == staged: {sec}", rel=1e-12 if fused else 0.0)
+    if scenario != "duplicates":
+        ref_t = fast_oracle.step_time_section({0: kept}, max_rows=W)
+        ref_m = fast_oracle.step_memory_section({0: kept}, window_size=W)
+        np.testing.assert_array_equal(ser[:12], ref_t["_series"][:12])
+        np.testing.assert_array_equal(mser[12:16], ref_m["_series"])
+        assert_struct(plain(got["step_time"]["data"]["aligned_window"]), plain(ref_t["data"]["aligned_window"]), "window")
+        assert_struct(plain(got["step_time"]["data"]["aligned_summary"]), plain(ref_t["data"]["aligned_summary"]), "sums")
+        assert_struct(plain(got["step_time"]["diagnosis"]), plain(ref_t["diagnosis"]), "diagnosis")
+        assert_struct(plain(got["step_time"]["global"]), plain(ref_t["global"]), "global")
+        assert plain(got["step_memory"]["per_global_rank"]) == plain(ref_m["per_global_rank"])
+        gd, rd = strip_device(plain(got["step_memory"]["diagnosis"])), strip_device(plain(ref_m["diagnosis"]))
+        assert_struct(gd["primary"], rd["primary"], "mem.primary")
+
+
 # ------------------------------------------------------------------------------------ (b)
 def test_step_memory_peaks_are_torch_exact(cuda):
     """a5: peak_alloc / peak_resv of every step == torch.cuda.max_memory_allocated / reserved

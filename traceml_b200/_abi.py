@@ -192,6 +192,8 @@ SIGNATURES = {
     "tml_struct_size": (u64, [C.c_char_p]),
     "tml_sections_json": (C.c_int, [C.POINTER(ReduceRunOut), C.POINTER(SectionsArgs), vp, C.c_size_t]),
     "tml_win_set_defer": (C.c_int, [vp, C.c_int]),
+    "tml_win_peek": (C.c_int, [vp, u32, C.POINTER(u64), C.POINTER(u64)]),
+    "tml_win_fused": (C.c_int, [vp, u32, vp, vp, C.POINTER(WinInfo), C.POINTER(AlignInfo), C.POINTER(u32)]),
     "tml_win_exact_collect": (C.c_int, [vp, vp, C.POINTER(f64)]),
     "tml_win_exact_stats": (C.c_int, [vp, C.POINTER(u64)]),
     "tml_xs_host_sum": (C.c_int, [vp, u64, C.c_int, C.POINTER(f64), C.POINTER(u64)]),

@@ -598,6 +598,181 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
 }
 
 
+
+// ------------------------------------------------------------------ K3a+K4 fused (single rank)
+// With ONE rank the cross-rank median and worst of a step are the rank's own value, so the
+// per-step series can be written straight from the ring records: 128 B in, 128 B out per step, and
+// the 64-B WindowRows -- written by K3a only to be re-read by K4 (r01: 256 MB each way at
+// W = 4e6, 1481 MB of DRAM traffic for 1024 MB of payload) -- never exist.  Same warp-private
+// cp.async pipeline as k_window_rows; lane = record, so each of the 16 series receives 32
+// consecutive doubles per tile: 256-B fully coalesced stores, no staging buffer.  Bounds, counters,
+// tree sums and maxima are produced exactly as in k_window_rows; the host accepts the series only
+// if the window turns out dense (every row a candidate of both kinds, consecutive step ids),
+// otherwise it falls back to the staged path.
+#define WF_WARP_U4 (2 * 32 * 8)
+#define WF_SMEM_BYTES (WR_WARPS * WF_WARP_U4 * 16)
+
+__global__ void __launch_bounds__(WR_THREADS, 2) k_window_fused(
+    const tml_step_record* __restrict__ ring, u32 ring_slots, u64 first_k, u64 n, u64 t_start,
+    double* __restrict__ series, u64 n_ser, WinAcc* acc, double* partials) {
+  extern __shared__ __align__(16) unsigned char wr_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint4* w_in0 = reinterpret_cast<uint4*>(wr_smem) + warp * WF_WARP_U4;
+  uint4* w_in1 = w_in0 + 32 * 8;
+
+  u64 a_lo0 = ~0ull, a_lo1 = ~0ull, a_hi0 = 0, a_hi1 = 0, a_latest = 0;
+  u32 a_nc0 = 0, a_nc1 = 0, a_nr0 = 0, a_nr1 = 0, a_viol = 0, a_dups = 0, a_tc = 0, a_both = 0;
+  u64 a_sa = 0, a_sr = 0;
+  double sums[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double mx_a = -INFINITY, mx_r = -INFINITY;
+  const u64 nwt = (n + 31) / 32;
+  const u64 wstride = (u64)gridDim.x * WR_WARPS;
+  const uint4* ring4 = reinterpret_cast<const uint4*>(ring);
+
+  u64 wt = (u64)blockIdx.x * WR_WARPS + warp;
+  u64 slot_cur = (first_k + wt * 32) % ring_slots;
+  const u64 slot_adv = (wstride * 32) % ring_slots;
+  if (wt < nwt) wr_issue_warp(w_in0, ring4, ring_slots, slot_cur, n, wt * 32, lane);
+  cp_async_commit();
+
+  for (int it = 0; wt < nwt; wt += wstride, ++it) {
+    uint4* cur = (it & 1) ? w_in1 : w_in0;
+    uint4* nxt = (it & 1) ? w_in0 : w_in1;
+    const u64 base = wt * 32;
+    const u64 next = wt + wstride;
+    u64 slot_next = slot_cur + slot_adv;
+    if (slot_next >= ring_slots) slot_next -= ring_slots;
+    if (next < nwt) wr_issue_warp(nxt, ring4, ring_slots, slot_next, n, next * 32, lane);
+    cp_async_commit();
+    u64 halo_step = 0;
+    u32 halo_flags = 0;
+    if (lane == 0 && base > 0) halo_step = ring[slot_cur == 0 ? ring_slots - 1 : slot_cur - 1].step;
+    if (lane == 31 && base + 32 < n) {
+      u64 hs = slot_cur + 32;
+      while (hs >= ring_slots) hs -= ring_slots;
+      const tml_step_record* p = &ring[hs];
+      halo_step = p->step; halo_flags = p->flags;
+    }
+    slot_cur = slot_next;
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const u64 i = base + (u64)lane;
+    const bool live = i < n;
+    const int sw = lane & 7;
+    const uint4 c0 = cur[lane * 8 + (0 ^ sw)], c1 = cur[lane * 8 + (1 ^ sw)];
+    const uint4 c2 = cur[lane * 8 + (2 ^ sw)], c3 = cur[lane * 8 + (3 ^ sw)];
+    const uint4 c5 = cur[lane * 8 + (5 ^ sw)], c6 = cur[lane * 8 + (6 ^ sw)];
+    const u64 step = (u64)c0.x | ((u64)c0.y << 32);
+    const u32 rflags = c6.w;
+    u64 prev_step = __shfl_up_sync(0xffffffffu, step, 1);
+    u64 next_step = __shfl_down_sync(0xffffffffu, step, 1);
+    u32 next_flags = __shfl_down_sync(0xffffffffu, rflags, 1);
+    if (lane == 0) prev_step = halo_step;
+    if (lane == 31) { next_step = halo_step; next_flags = halo_flags; }
+
+    if (live) {
+      const u64 d0 = (u64)c0.z | ((u64)c0.w << 32);
+      const u64 d2 = (u64)c1.z | ((u64)c1.w << 32);
+      const u64 d3 = (u64)c2.x | ((u64)c2.y << 32);
+      const u64 d4 = (u64)c2.z | ((u64)c2.w << 32);
+      const u64 d5 = (u64)c3.x | ((u64)c3.y << 32);
+      const u64 pa = (u64)c5.x | ((u64)c5.y << 32);
+      const u64 pr = (u64)c5.z | ((u64)c5.w << 32);
+      const double dl = ns_to_ms(d0), fwd = ns_to_ms(d2);
+      const double bwd = ns_to_ms(d3), opt = ns_to_ms(d4), wall = ns_to_ms(d5);
+      const bool has_mem = (rflags & TML_REC_HAS_MEM) != 0u;
+      const bool usable = (dl > 0.0) || (fwd > 0.0) || (bwd > 0.0) || (opt > 0.0) || (wall > 0.0);
+      const bool in_time = i >= t_start;
+      const bool has_prev = i > 0, has_next = (i + 1) < n;
+      const bool first_in_win = (i == t_start) || !has_prev || (prev_step != step);
+      const bool last_m = !has_next || (next_step != step) || ((next_flags & TML_REC_HAS_MEM) == 0u);
+      const bool cand_t = usable && in_time && first_in_win;
+      const bool cand_m = has_mem && last_m;
+      a_latest = step > a_latest ? step : a_latest;
+      a_viol += (has_prev && step < prev_step) ? 1u : 0u;
+      a_dups += (has_prev && step == prev_step) ? 1u : 0u;
+      a_nr0 += in_time ? 1u : 0u;
+      a_nr1 += has_mem ? 1u : 0u;
+      if (cand_t) { a_lo0 = step < a_lo0 ? step : a_lo0; a_hi0 = step > a_hi0 ? step : a_hi0; ++a_nc0; }
+      if (cand_m) { a_lo1 = step < a_lo1 ? step : a_lo1; a_hi1 = step > a_hi1 ? step : a_hi1; ++a_nc1; }
+      a_both += (cand_t && cand_m) ? 1u : 0u;
+      const double compute = (fwd + bwd) + opt;
+      const double traced = fmax(wall, compute);      // model.py:246
+      if (usable && in_time) {
+        sums[0] += dl; sums[1] += fwd; sums[2] += bwd; sums[3] += opt;
+        sums[4] += wall; sums[5] += traced; sums[6] += dl + traced;
+        ++a_tc;
+      }
+      if (in_time) {
+        a_sa += pa; a_sr += pr;
+        mx_a = fmax(mx_a, (double)pa); mx_r = fmax(mx_r, (double)pr);
+        // one rank: median == worst == the value (adapters.py:92-139 with a single column)
+        const u64 j = i - t_start;
+        const double wait = fmax(0.0, traced - compute);  // model.py:247
+        const double va = (double)pa, vr = (double)pr;
+        double* S = series + j;
+        S[0 * n_ser] = dl;     S[1 * n_ser] = dl;
+        S[2 * n_ser] = fwd;    S[3 * n_ser] = fwd;
+        S[4 * n_ser] = bwd;    S[5 * n_ser] = bwd;
+        S[6 * n_ser] = opt;    S[7 * n_ser] = opt;
+        S[8 * n_ser] = traced; S[9 * n_ser] = traced;
+        S[10 * n_ser] = wait;  S[11 * n_ser] = wait;
+        S[12 * n_ser] = va;    S[13 * n_ser] = va;
+        S[14 * n_ser] = vr;    S[15 * n_ser] = vr;
+      }
+    }
+    __syncwarp();  // `cur` is free again
+  }
+  cp_async_wait<0>();
+  {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      u64 t;
+      t = __shfl_xor_sync(0xffffffffu, a_lo0, m); a_lo0 = t < a_lo0 ? t : a_lo0;
+      t = __shfl_xor_sync(0xffffffffu, a_lo1, m); a_lo1 = t < a_lo1 ? t : a_lo1;
+      t = __shfl_xor_sync(0xffffffffu, a_hi0, m); a_hi0 = t > a_hi0 ? t : a_hi0;
+      t = __shfl_xor_sync(0xffffffffu, a_hi1, m); a_hi1 = t > a_hi1 ? t : a_hi1;
+      t = __shfl_xor_sync(0xffffffffu, a_latest, m); a_latest = t > a_latest ? t : a_latest;
+      a_sa += __shfl_xor_sync(0xffffffffu, a_sa, m); a_sr += __shfl_xor_sync(0xffffffffu, a_sr, m);
+    }
+    a_nc0 = __reduce_add_sync(0xffffffffu, a_nc0); a_nc1 = __reduce_add_sync(0xffffffffu, a_nc1);
+    a_nr0 = __reduce_add_sync(0xffffffffu, a_nr0); a_nr1 = __reduce_add_sync(0xffffffffu, a_nr1);
+    a_viol = __reduce_add_sync(0xffffffffu, a_viol); a_dups = __reduce_add_sync(0xffffffffu, a_dups);
+    a_tc = __reduce_add_sync(0xffffffffu, a_tc); a_both = __reduce_add_sync(0xffffffffu, a_both);
+    if (lane == 0) {
+      if (a_nc0) { atomicMin(&acc->lo[0], a_lo0); atomicMax(&acc->hi[0], a_hi0); atomicAdd(&acc->ncand[0], (u64)a_nc0); }
+      if (a_nc1) { atomicMin(&acc->lo[1], a_lo1); atomicMax(&acc->hi[1], a_hi1); atomicAdd(&acc->ncand[1], (u64)a_nc1); }
+      if (a_nr0) atomicAdd(&acc->nrows[0], (u64)a_nr0);
+      if (a_nr1) atomicAdd(&acc->nrows[1], (u64)a_nr1);
+      atomicMax(&acc->latest_step, a_latest);
+      if (a_viol) atomicAdd(&acc->violations, (u64)a_viol);
+      if (a_dups) atomicAdd(&acc->dups, (u64)a_dups);
+      if (a_tc) atomicAdd(&acc->t_count, (u64)a_tc);
+      if (a_both) atomicAdd(&acc->n_both, (u64)a_both);
+      if (a_sa) atomicAdd(&acc->msum[0], a_sa);
+      if (a_sr) atomicAdd(&acc->msum[1], a_sr);
+    }
+  }
+  __syncthreads();
+  block_sum<9, WR_THREADS>(sums, partials + (size_t)blockIdx.x * 11);
+  {
+    __shared__ double s_mx[WR_THREADS / 32][2];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      mx_a = fmax(mx_a, shfl_xor_f64(mx_a, m));
+      mx_r = fmax(mx_r, shfl_xor_f64(mx_r, m));
+    }
+    if (lane == 0) { s_mx[warp][0] = mx_a; s_mx[warp][1] = mx_r; }
+    __syncthreads();
+    if (tid < 2) {
+      double x = -INFINITY;
+      for (int w = 0; w < WR_THREADS / 32; ++w) x = fmax(x, s_mx[w][tid]);
+      partials[(size_t)blockIdx.x * 11 + 9 + tid] = x;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ K3b: presence
 
 __global__ void k_presence(const u64* __restrict__ steps, const u8* __restrict__ flags, u64 n,
@@ -1741,6 +1916,97 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   if (!out->monotone)
     return set_err(TML_ERR_NONMONOTONIC, "step ids decrease inside the retained ring (%llu places)",
                    acc.violations);
+  return TML_OK;
+}
+
+int tml_win_peek(tml_ctx* c, uint32_t window, uint64_t* n_retained, uint64_t* n_window) {
+  if (!c || window == 0) return TML_ERR_ARG;
+  const u64 n = c->commits < c->ring_slots ? c->commits : c->ring_slots;
+  if (n_retained) *n_retained = n;
+  if (n_window) *n_window = n > window ? window : n;
+  return TML_OK;
+}
+
+// Single-rank bulk path: ring -> per-step series in ONE pass (k_window_fused).  *ok = 1: the
+// window is dense and `series` ([16][n_window], device) plus `aligned` hold the result; 0: the
+// caller runs the staged path (tml_win_prepare ...).  Leaves no WindowRows behind.
+int tml_win_fused(tml_ctx* c, uint32_t window, double* series, void* stream, tml_win_info* out,
+                  tml_align_info* aligned, uint32_t* ok) {
+  if (!c || !out || !aligned || !ok || !series || window == 0) return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  memset(aligned, 0, sizeof(*aligned));
+  *ok = 0;
+  const u64 n = c->commits < c->ring_slots ? c->commits : c->ring_slots;
+  const u64 first_k = c->commits - n;
+  const u64 t_start = n > window ? n - window : 0;
+  const u64 n_win = n - t_start;
+  c->win_ready = false;
+  out->n_retained = n;
+  out->monotone = 1;
+  if (n == 0) return TML_OK;
+  if (c->xs_pending) { CK(cudaStreamWaitEvent(s, c->xs_done, 0)); c->xs_pending = false; }
+  WinAcc init;
+  memset(&init, 0, sizeof(init));
+  init.lo[0] = init.lo[1] = ~0ull;
+  CK(cudaMemcpyAsync(c->d_winacc, &init, sizeof(init), cudaMemcpyHostToDevice, s));
+  static bool wf_attr = false;
+  if (!wf_attr) {
+    CK(cudaFuncSetAttribute(k_window_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, WF_SMEM_BYTES));
+    wf_attr = true;
+  }
+  int grid = (int)((n + WR_THREADS - 1) / WR_THREADS);
+  if (grid > c->n_sms * 2) grid = c->n_sms * 2;
+  if (!c->ev0) { CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); }
+  CK(cudaEventRecord(c->ev0, s));
+  k_window_fused<<<grid, WR_THREADS, WF_SMEM_BYTES, s>>>(c->d_ring, c->ring_slots, first_k, n, t_start, series, n_win,
+                                                          c->d_winacc, c->d_partials);
+  CK(cudaPeekAtLastError());
+  CK(cudaEventRecord(c->ev1, s));
+  k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
+  CK(cudaPeekAtLastError());
+  c->launches += 2;
+  char* st = (char*)c->h_stage;
+  CK(cudaMemcpyAsync(st + 1024, c->d_final, 64 * sizeof(double) + sizeof(WinAcc), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  WinAcc acc;
+  memcpy(&acc, st + 1024 + 64 * sizeof(double), sizeof(acc));
+  double f[11];
+  memcpy(f, st + 1024 + 32 * sizeof(double), sizeof(f));
+  memcpy(out->t_sums, f, 7 * sizeof(double));
+  out->latest_step = acc.latest_step;
+  out->monotone = acc.violations == 0 ? 1u : 0u;
+  out->dup_rows = (u32)acc.dups;
+  const u64 rows_in[2] = {n_win, n};
+  for (int k = 0; k < 2; ++k) {
+    out->n_rows[k] = acc.nrows[k];
+    out->n_cand[k] = acc.ncand[k];
+    out->lo[k] = acc.ncand[k] ? acc.lo[k] : 0;
+    out->hi[k] = acc.ncand[k] ? acc.hi[k] : 0;
+    out->dense[k] = (acc.ncand[k] > 0 && acc.ncand[k] == rows_in[k] &&
+                     (out->hi[k] - out->lo[k] + 1) == acc.ncand[k]) ? 1u : 0u;
+  }
+  out->t_count = acc.t_count;
+  out->n_both = acc.n_both;
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) out->kernel_ms = (double)ms;
+  }
+  if (!out->monotone)
+    return set_err(TML_ERR_NONMONOTONIC, "step ids decrease inside the retained ring (%llu places)", acc.violations);
+  // dense in both kinds: the last min(n, W) memory candidates are exactly the time window's rows
+  if (out->dense[0] && out->dense[1] && out->hi[0] == out->hi[1] && acc.ncand[0] == n_win) {
+    *ok = 1;
+    aligned->n_common = n_win;
+    aligned->start_step = out->lo[0];
+    aligned->end_step = out->hi[0];
+    aligned->n_rows = n_win;
+    memcpy(aligned->t_sums, out->t_sums, 7 * sizeof(double));
+    aligned->t_sums[4] = out->t_sums[5];  // aligned step_cpu = sum of traced (alignment.py:72)
+    aligned->m_sums[0] = (double)acc.msum[0]; aligned->m_sums[1] = (double)acc.msum[1];
+    aligned->m_sums[2] = f[9]; aligned->m_sums[3] = f[10];
+  }
   return TML_OK;
 }
 

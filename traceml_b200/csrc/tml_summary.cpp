@@ -247,6 +247,7 @@ bool trend_layout(u64 n, u64 min_points, double warmup_frac, u64 lo[3], u64 hi[3
 }
 
 // ------------------------------------------------------------------ the run
+constexpr u64 TML_FUSED_MIN_ROWS = 1u << 17;  // == TML_EXACT_SUM_MAX: below it the staged path gives reference-order sums
 constexpr u64 P2P_MIN_ROWS = 1000000;  // reduce.py: one-shot IPC mapping (44-65 ms at R = 8) pays above this
 
 struct KindState {
@@ -487,6 +488,53 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
     CKC(cudaEventRecord(r.w->side_gate, r.s));
     CKC(cudaStreamWaitEvent(r.w->side, r.w->side_gate, 0));
     CKT(tml_proc_reduce_launch(c, args->proc_rows, r.w->side));
+  }
+  // ---- single rank, bulk window: ring -> series in ONE pass (k_window_fused); the WindowRows
+  // that K3a would write for K4 to re-read never exist.  Falls through to the staged path when the
+  // window is not dense (re-flushed step ids, rows without memory, ...).
+  if (world == 1) {
+    u64 n_ret = 0, n_win = 0;
+    CKT(tml_win_peek(c, window, &n_ret, &n_win));
+    if (n_win > (u64)TML_FUSED_MIN_ROWS) {
+      CKT(grow(&r.w->d_series[0], &r.w->cap_series[0], (u64)TML_SERIES_PER_STEP * n_win));
+      tml_win_info finfo;
+      tml_align_info fal;
+      uint32_t ok = 0;
+      CKT(tml_win_fused(c, window, r.w->d_series[0], r.s, &finfo, &fal, &ok));
+      if (ok) {
+        tml_proc_agg pagg0;
+        memset(&pagg0, 0, sizeof(pagg0));
+        if (args->proc_rows) CKT(tml_proc_reduce_collect(c, &pagg0));
+        out->n_ranks = 1;
+        out->infos[0] = finfo;
+        out->procs[0] = pagg0;
+        for (tml_kind_result* res : {&out->time, &out->mem}) {
+          res->observed = 1; res->n_used = 1; res->used[0] = 0;
+          res->n_common = fal.n_common; res->start_step = fal.start_step; res->end_step = fal.end_step;
+          res->n_rows[0] = fal.n_rows;
+          memcpy(res->t_sums[0], fal.t_sums, sizeof(fal.t_sums));
+          memcpy(res->m_sums[0], fal.m_sums, sizeof(fal.m_sums));
+          res->series = r.w->d_series[0];
+          res->shard_lo = 0; res->shard_hi = fal.n_common;
+        }
+        out->exchange_used = TML_XCHG_LOCAL;
+        out->fused_pass = 2;  // 2: K3a and K4 fused as well (no WindowRows)
+        const double tf = now_ms();
+        CKT(bands(r, &out->time));
+        memcpy(out->mem.band_sum, out->time.band_sum, sizeof(out->time.band_sum));
+        memcpy(out->mem.band_cnt, out->time.band_cnt, sizeof(out->time.band_cnt));
+        memcpy(out->mem.tail_first, out->time.tail_first, sizeof(out->time.tail_first));
+        memcpy(out->mem.tail_last, out->time.tail_last, sizeof(out->time.tail_last));
+        out->mem.has_bands = out->time.has_bands;
+        const double te = now_ms();
+        out->n_exchanges = r.n_exchanges;
+        out->k3a_ms = finfo.kernel_ms;
+        out->k4_ms = 0.0;
+        out->stage_ms[0] = tf - t0; out->stage_ms[1] = 0.0; out->stage_ms[2] = 0.0;
+        out->stage_ms[3] = te - tf; out->stage_ms[4] = te - t0;
+        return TML_OK;
+      }
+    }
   }
   tml_win_info info;
   // R > 1: K3e (reference-order sums) runs beside the exchanges and K4; its result is collected

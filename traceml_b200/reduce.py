@@ -208,6 +208,7 @@ class NativeReduceOutput:
         self.window = window
         self.exchange = _abi.XCHG_NAME[int(o.exchange_used)]
         self.fused_pass = bool(o.fused_pass)
+        self.fused_rows = int(o.fused_pass) == 2  # single-rank bulk path: ring -> series in one kernel
         self.timings_ms = reducer.native_timings(o)
         self.n_exchanges = int(o.n_exchanges)
         self.ranks = list(range(int(o.n_ranks)))
