@@ -283,8 +283,63 @@ def sections_json(run_out, ram_total: float, gpu_count: int, window: int, proc_r
         _SEC_BUF = C.create_string_buffer(len(_SEC_BUF) * 8)
         return sections_json(run_out, ram_total, gpu_count, window, proc_rows)
     check(rc, "tml_sections_json")
-    res = json.loads(_SEC_BUF.value)
-    data = res["step_time"]["data"]
-    for key in ("aligned_summary", "per_global_rank_summary"):
-        data[key] = {int(k): v for k, v in data[key].items()}
-    return res
+    return Sections(_SEC_BUF.value)
+
+
+class Sections:
+    """The three sections of one reduce: a read-only mapping over the JSON text the native emitter
+    produced.  The text is the product (it is what ``final_summary.json`` stores); the Python
+    objects are a view of it, built on first access -- a summary that is only written to disk, or
+    only asked for its diagnosis label, never pays for the rest.  ``reduce`` (the raw reduce
+    output) and anything else the caller attaches live beside the parsed sections."""
+
+    __slots__ = ("raw", "_parsed", "_extra")
+
+    def __init__(self, raw: bytes):
+        self.raw = raw
+        self._parsed = None
+        self._extra = {}
+
+    def _get(self):
+        if self._parsed is None:
+            res = json.loads(self.raw)
+            data = res["step_time"]["data"]
+            for key in ("aligned_summary", "per_global_rank_summary"):  # rank-keyed tables: int keys back
+                data[key] = {int(k): v for k, v in data[key].items()}
+            self._parsed = res
+        return self._parsed
+
+    def __getitem__(self, key):
+        if key in self._extra:
+            return self._extra[key]
+        return self._get()[key]
+
+    def __setitem__(self, key, value):
+        self._extra[key] = value
+
+    def __contains__(self, key):
+        return key in self._extra or key in self._get()
+
+    def __iter__(self):
+        yield from self._get()
+        yield from self._extra
+
+    def __len__(self):
+        return len(self._get()) + len(self._extra)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def keys(self):
+        return list(self)
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def pop(self, key, *default):
+        if key in self._extra:
+            return self._extra.pop(key)
+        return self._get().pop(key, *default)
+
+    def to_dict(self):
+        return dict(self.items())

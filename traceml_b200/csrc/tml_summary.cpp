@@ -14,7 +14,13 @@
 // torch.distributed uses): no link-time dependency, no second NCCL in the process.
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
 
 #include <chrono>
 #include <cmath>
@@ -107,7 +113,38 @@ struct RunWs {
   bool p2p_warm = false;  // peer mappings already open: peer loads cost nothing extra
   cudaStream_t side = nullptr;  // process aggregates (K6) run beside K3a, not in front of it
   cudaEvent_t side_gate = nullptr;  // side waits for what `stream` held at entry (ring loads)
+  // host mailbox for the small exchanges (ranks of one node): see Run::xchg
+  bool mbox_tried = false;
+  void* mbox = nullptr;
+  size_t mbox_bytes = 0;
+  u64 mbox_seq = 0;
 };
+
+// ------------------------------------------------------------------ host mailbox
+// The small exchanges carry HOST data (bounds, counts, sums: a few hundred bytes per rank that
+// the stage before has just synchronised onto the host).  Round 1 sent them through the GPU and
+// back -- pinned H2D, ncclAllGather, D2H, stream sync: ~70 us each, three per reduce, a fifth of
+// the N = 8 step.  All ranks of this engine's scope live on one node, so they meet in a POSIX
+// shared-memory segment instead: rank p writes its vector into slot p of a double-buffered
+// mailbox and publishes a sequence number with release semantics; everybody spins (acquire) until
+// all R slots carry the current number.  A few microseconds, no GPU work, no stream sync.
+// Set up once per context by two NCCL all-gathers (token + host check, then "opened"); ranks on
+// different hosts, or a failed shm_open, keep the NCCL path.
+constexpr int MB_DOUBLES = 192;
+struct MboxSlot {
+  std::atomic<u64> seq[2];
+  double data[2][MB_DOUBLES];
+};
+static_assert(sizeof(std::atomic<u64>) == 8, "lock-free 64-bit atomics");
+
+u64 host_hash() {
+  char name[256];
+  memset(name, 0, sizeof(name));
+  gethostname(name, sizeof(name) - 1);
+  u64 h = 1469598103934665603ull;
+  for (const char* p = name; *p; ++p) { h ^= (unsigned char)*p; h *= 1099511628211ull; }
+  return h & ((1ull << 52) - 1);  // travels as a double
+}
 
 int ensure_ws(tml_ctx* c, RunWs** out) {
   void** slot = tml_run_ws_slot_(c);
@@ -143,11 +180,92 @@ struct Run {
   int rank, world;
   u32 n_exchanges = 0;
 
+  int nccl_gather(const double* vec, int len, double* all) {
+    memcpy(w->h_send, vec, (size_t)len * sizeof(double));
+    CKC(cudaMemcpyAsync(w->d_send, w->h_send, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, s));
+    CKN(g_nccl.AllGather(w->d_send, w->d_recv, (size_t)len, ncclDouble, (ncclComm_t)comm->nccl_comm, s));
+    CKC(cudaMemcpyAsync(w->h_recv, w->d_recv, (size_t)len * world * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    memcpy(all, w->h_recv, (size_t)len * world * sizeof(double));
+    return TML_OK;
+  }
+
+  // once per context: agree on a shared-memory mailbox (all ranks on one host), else stay on NCCL
+  int mbox_setup() {
+    w->mbox_tried = true;
+    const char* off = getenv("TML_NO_MAILBOX");
+    const bool disabled = off && off[0] == '1';
+    double mine[4] = {(double)host_hash(), (double)getpid(), 0.0, disabled ? 1.0 : 0.0};
+    if (rank == 0) {
+      u64 t = (u64)std::chrono::steady_clock::now().time_since_epoch().count();
+      mine[2] = (double)((t ^ ((u64)getpid() << 20)) & ((1ull << 50) - 1));
+    }
+    std::vector<double> all((size_t)world * 4);
+    CKT(nccl_gather(mine, 4, all.data()));
+    bool same = true;
+    for (int p = 0; p < world; ++p) same = same && all[(size_t)p * 4] == all[0] && all[(size_t)p * 4 + 3] == 0.0;
+    char name[96];
+    snprintf(name, sizeof(name), "/tml_b200_%llu_%llu", (unsigned long long)all[1], (unsigned long long)all[2]);
+    const size_t bytes = sizeof(MboxSlot) * (size_t)world;
+    void* mem = nullptr;
+    int fd = -1;
+    if (same && rank == 0) {
+      fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+      if (fd >= 0 && ftruncate(fd, (off_t)bytes) == 0) {
+        mem = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (mem == MAP_FAILED) mem = nullptr;
+        else memset(mem, 0, bytes);
+      }
+    }
+    double ok1[1] = {(!same || rank != 0 || mem) ? 1.0 : 0.0};
+    std::vector<double> oks((size_t)world);
+    CKT(nccl_gather(ok1, 1, oks.data()));  // rank 0 has created the segment (or given up)
+    bool go = same && oks[0] == 1.0;
+    if (go && rank != 0) {
+      fd = shm_open(name, O_RDWR, 0600);
+      if (fd >= 0) {
+        mem = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (mem == MAP_FAILED) mem = nullptr;
+      }
+    }
+    if (fd >= 0) close(fd);
+    double ok2[1] = {(!go || mem) ? 1.0 : 0.0};
+    CKT(nccl_gather(ok2, 1, oks.data()));  // everybody has mapped it: the name can go
+    if (rank == 0 && same) shm_unlink(name);
+    for (int p = 0; p < world; ++p) go = go && oks[p] == 1.0;
+    if (go && mem) { w->mbox = mem; w->mbox_bytes = bytes; w->mbox_seq = 0; }
+    else if (mem) munmap(mem, bytes);
+    return TML_OK;
+  }
+
+  int mbox_gather(const double* vec, int len, double* all) {
+    MboxSlot* slots = (MboxSlot*)w->mbox;
+    const u64 seq = ++w->mbox_seq;
+    const int b = (int)(seq & 1ull);
+    memcpy(slots[rank].data[b], vec, (size_t)len * sizeof(double));
+    slots[rank].seq[b].store(seq, std::memory_order_release);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int p = 0; p < world; ++p) {
+      unsigned spins = 0;
+      while (slots[p].seq[b].load(std::memory_order_acquire) < seq) {
+        if ((++spins & 0xfffu) == 0u) {
+          if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60))
+            return tml_set_error_(TML_ERR_STATE, "mailbox exchange %llu: rank %d never arrived", (unsigned long long)seq, p);
+          sched_yield();
+        }
+      }
+      memcpy(all + (size_t)p * len, slots[p].data[b], (size_t)len * sizeof(double));
+    }
+    return TML_OK;
+  }
+
   // one small exchange: every rank contributes `len` doubles; all[r * len + i]
   int xchg(const double* vec, int len, double* all) {
     ++n_exchanges;
     if (world == 1) { memcpy(all, vec, (size_t)len * sizeof(double)); return TML_OK; }
     if (len > XV) return tml_set_error_(TML_ERR_ARG, "exchange vector too long (%d)", len);
+    if (!w->mbox_tried) CKT(mbox_setup());
+    if (w->mbox && len <= MB_DOUBLES) return mbox_gather(vec, len, all);
     memcpy(w->h_send, vec, (size_t)len * sizeof(double));
     CKC(cudaMemcpyAsync(w->d_send, w->h_send, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, s));
     CKN(g_nccl.AllGather(w->d_send, w->d_recv, (size_t)len, ncclDouble, (ncclComm_t)comm->nccl_comm, s));
@@ -681,6 +799,7 @@ extern "C" void tml_run_ws_free_(void* p) {
   cudaFree(w->d_send); cudaFree(w->d_recv); cudaFreeHost(w->h_send); cudaFreeHost(w->h_recv);
   cudaFree(w->d_presence); cudaFree(w->d_series[0]); cudaFree(w->d_series[1]);
   cudaFree(w->d_recv_rows); cudaFree(w->d_zero_rows);
+  if (w->mbox) munmap(w->mbox, w->mbox_bytes);
   if (w->side) cudaStreamDestroy(w->side);
   if (w->side_gate) cudaEventDestroy(w->side_gate);
   delete w;
