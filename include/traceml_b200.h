@@ -142,9 +142,11 @@ int tml_phase_end(tml_ctx* ctx, uint32_t phase, int slot, void* stream);
  * Replaces timed_region(use_gpu=False): utils/timing.py:211-213,236-244. */
 int tml_phase_host(tml_ctx* ctx, uint32_t phase, uint64_t dur_ns);
 /* Close the step: commit kernel stages the in-flight record through shared
- * memory, merges the host-clock phases, reads the allocator peaks from the
- * host-mapped counter page, writes one coalesced 128-B line into the HBM ring
- * (and the drain mirror), updates the running statistics, bumps the head.
+ * memory, merges the host-clock phases and the allocator peaks (c10 allocator
+ * counters are host state: they travel as launch arguments), writes one
+ * coalesced 128-B line into the HBM ring, updates the running statistics and
+ * bumps the head.  It writes NOTHING to host memory and issues no system-scope
+ * fence: the training stream pays for the record, not for the sampler.
  * Replaces StepMemoryTracker.record + flush_step_events:
  * utils/step_memory.py:60-110, utils/flush_buffers.py:24-33,
  * utils/timing.py:163-180. */
@@ -157,7 +159,10 @@ int tml_step_discard(tml_ctx* ctx);
 /* ------------------------------------------------------- SAMPLER-SIDE (host)
  * Called from the sampler thread; never touches the training stream. */
 
-/* Non-blocking drain of completed records from the host-mapped mirror.
+/* Drain of completed records.  The sampler fetches them itself: one small copy
+ * kernel (k_mirror) on the context's own sampler stream brings the records
+ * committed since the last call -- and the live statistics -- into a host-mapped
+ * mirror; the call waits for that stream only, never for the training stream.
  * Replaces StepTimeSampler.sample + StepMemorySampler.sample:
  * samplers/step_time_sampler.py:104-128, samplers/step_memory_sampler.py:12-65. */
 int tml_drain(tml_ctx* ctx, tml_step_record* out, uint32_t max_records,

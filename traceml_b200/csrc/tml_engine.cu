@@ -45,7 +45,6 @@ static_assert(sizeof(tml_proc_record) == 64, "ProcRecord must be 64 B");
 
 #define TML_N_SLOTS 64u      // begin-timestamp slots (regions in flight)
 #define TML_N_EPOCHS 8u      // in-flight accumulator sets (steps in flight)
-#define TML_MEMSTAT_SLOTS 4096u
 #define TML_HIST_BINS 256u
 
 // row flags written by k_window_rows
@@ -72,6 +71,7 @@ struct DevState {
   u64 live_sum[TML_MAX_PHASES];
   u64 live_max[TML_MAX_PHASES];
   u32 hist[TML_N_PHASES][TML_HIST_BINS];
+  tml_live_stats live;  // running count / sum / worst / median per phase (k_mirror copies it out)
 };
 
 // host-mapped page: written by kernels, read by the sampler thread with no CUDA call
@@ -79,7 +79,6 @@ struct HostPage {
   volatile u64 mirror_head;
   volatile u64 pmirror_head;
   tml_live_stats live;
-  u64 memstat[TML_MEMSTAT_SLOTS][2];  // allocator peak counters, written by the host at commit
 };
 
 struct CommitArgs {
@@ -89,8 +88,8 @@ struct CommitArgs {
   u32 host_calls[TML_MAX_PHASES];
   u32 epoch;
   u32 flags;
-  u32 memslot;
-  u32 _pad;
+  u64 peak_alloc;  // c10 allocator peaks of the step (host state: they travel as launch arguments)
+  u64 peak_resv;
 };
 
 struct WinAcc {  // integer side results of k_window_rows (atomics; order-independent)
@@ -159,9 +158,12 @@ __global__ void k_stamp_end(DevState* st, u32 slot, u32 phase, u32 epoch) {
 // 6 warps: warp p owns phase p's running statistics; warp 0 also assembles the
 // 128-B record in shared memory and writes it as 8 x 16-B coalesced stores.
 
+// Nothing in here leaves the GPU: round 1 also wrote the record and the live statistics into
+// host-mapped memory and closed with __threadfence_system -- 7.6 us of the TRAINING stream per step
+// (r01 launch list) for the benefit of a sampler that looks twice a second.  The sampler now
+// fetches what it needs itself (k_mirror, on its own stream, tml_drain / tml_live).
 __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* ring, u32 ring_slots,
-                                                 tml_step_record* mirror, u32 mirror_slots,
-                                                 HostPage* page, CommitArgs a) {
+                                                 CommitArgs a) {
   __shared__ __align__(16) u64 rec[16];
   __shared__ u64 s_dur[TML_MAX_PHASES];
   __shared__ u32 s_calls[TML_MAX_PHASES];
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* r
       mx = dur > mx ? dur : mx;
       st->live_sum[warp] = sum;
       st->live_max[warp] = mx;
-      tml_live_phase* lp = &page->live.phase[warp];
+      tml_live_phase* lp = &st->live.phase[warp];
       lp->count = total;
       lp->sum_ns = sum;
       lp->worst_ns = mx;
@@ -237,9 +239,7 @@ __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* r
     u64 seq = 0;
     if (lane == 0) {
       seq = st->head;
-      const u64* ms = page->memstat[a.memslot];
-      u64 peak_alloc = ((const volatile u64*)ms)[0];
-      u64 peak_resv = ((const volatile u64*)ms)[1];
+      const u64 peak_alloc = a.peak_alloc, peak_resv = a.peak_resv;
       rec[0] = a.step;
 #pragma unroll
       for (int p = 0; p < 6; ++p) rec[1 + p] = s_dur[p];
@@ -258,16 +258,39 @@ __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* r
     if (lane < 8) {
       uint4 v = reinterpret_cast<const uint4*>(rec)[lane];
       reinterpret_cast<uint4*>(&ring[seq % ring_slots])[lane] = v;
-      reinterpret_cast<uint4*>(&mirror[seq % mirror_slots])[lane] = v;
     }
     __syncwarp();
     if (lane == 0) {
-      __threadfence_system();
+      __threadfence();  // the record is visible to every later reader of `head` on this GPU
+      st->live.steps_committed = seq + 1;
       st->head = seq + 1;
-      page->live.steps_committed = seq + 1;
-      page->mirror_head = seq + 1;
     }
   }
+}
+
+// Sampler side: copy the records committed since `from` (at most the newest mirror_slots) and the
+// live statistics into host-mapped memory.  One CTA, on the sampler's own stream; the caller
+// synchronises that stream, so no system-scope fence is needed here either.
+__global__ void __launch_bounds__(1024) k_mirror(const DevState* st, const tml_step_record* __restrict__ ring,
+                                                  u32 ring_slots, tml_step_record* mirror, u32 mirror_slots,
+                                                  HostPage* page, u64 from) {
+  __shared__ u64 s_head;
+  if (threadIdx.x == 0) s_head = *reinterpret_cast<const volatile u64*>(&st->head);
+  __syncthreads();
+  const u64 head = s_head;
+  if (head - from > (u64)mirror_slots) from = head - mirror_slots;
+  const u64 n16 = (head - from) * 8ull;  // 16-B pieces
+  for (u64 k = threadIdx.x; k < n16; k += blockDim.x) {
+    const u64 seq = from + (k >> 3);
+    const int q = (int)(k & 7);
+    reinterpret_cast<uint4*>(&mirror[seq % mirror_slots])[q] =
+        reinterpret_cast<const uint4*>(&ring[seq % ring_slots])[q];
+  }
+  const int nl = (int)(sizeof(tml_live_stats) / 8);
+  for (int k = threadIdx.x; k < nl; k += blockDim.x)
+    reinterpret_cast<volatile u64*>(&page->live)[k] = reinterpret_cast<const volatile u64*>(&st->live)[k];
+  __syncthreads();
+  if (threadIdx.x == 0) page->mirror_head = head;
 }
 
 // ------------------------------------------------------------------ K5: proc commit
@@ -1358,6 +1381,9 @@ struct tml_ctx {
   // sampler-thread state
   std::atomic<u64> proc_commits{0};
   u64 drain_tail = 0, pdrain_tail = 0;
+  u64 mirror_copied = 0;            // records k_mirror has brought to the host so far
+  cudaStream_t drain_stream = nullptr;
+  std::mutex mirror_mu;
   std::mutex proc_mu;
   // reduce workspace
   u64 cap_rows = 0;
@@ -1555,6 +1581,7 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
   cudaFree(c->d_noncontig); cudaFree(c->d_gacc);
   cudaFree(c->d_xs_buf); cudaFree(c->d_xs_out); cudaFree(c->d_xs_stats);
+  if (c->drain_stream) cudaStreamDestroy(c->drain_stream);
   if (c->xs_stream) cudaStreamDestroy(c->xs_stream);
   if (c->xs_gate) cudaEventDestroy(c->xs_gate);
   if (c->xs_done) cudaEventDestroy(c->xs_done);
@@ -1638,14 +1665,9 @@ int tml_step_commit(tml_ctx* c, uint64_t step, uint64_t peak_alloc, uint64_t pea
   memcpy(a.host_calls, c->host_calls, sizeof(a.host_calls));
   a.epoch = (u32)(c->commits % TML_N_EPOCHS);
   a.flags = flags;
-  a.memslot = (u32)(c->commits % TML_MEMSTAT_SLOTS);
-  a._pad = 0;
-  // allocator peak counters go through the host-mapped counter page; the kernel reads them
-  c->h_page->memstat[a.memslot][0] = peak_alloc;
-  c->h_page->memstat[a.memslot][1] = peak_resv;
-  std::atomic_thread_fence(std::memory_order_release);
-  k_commit<<<1, 192, 0, s>>>(c->d_state, c->d_ring, c->ring_slots, c->d_mirror, c->mirror_slots,
-                              c->d_page, a);
+  a.peak_alloc = peak_alloc;
+  a.peak_resv = peak_resv;
+  k_commit<<<1, 192, 0, s>>>(c->d_state, c->d_ring, c->ring_slots, a);
   memset(c->host_dur, 0, sizeof(c->host_dur));
   memset(c->host_calls, 0, sizeof(c->host_calls));
   if (cudaPeekAtLastError() != cudaSuccess)
@@ -1662,9 +1684,26 @@ uint64_t tml_proc_count(tml_ctx* c) { return c ? c->proc_commits.load() : 0; }
 
 // ---------------------------------------------------------------- sampler side
 
+// bring the host mirror up to date (sampler thread, own stream; never the training stream)
+static int refresh_mirror(tml_ctx* c) {
+  DeviceGuard dg(c);
+  std::lock_guard<std::mutex> g(c->mirror_mu);
+  if (!c->drain_stream) CK(cudaStreamCreateWithFlags(&c->drain_stream, cudaStreamNonBlocking));
+  k_mirror<<<1, 1024, 0, c->drain_stream>>>(c->d_state, c->d_ring, c->ring_slots, c->d_mirror, c->mirror_slots,
+                                            c->d_page, c->mirror_copied);
+  CK(cudaPeekAtLastError());
+  CK(cudaStreamSynchronize(c->drain_stream));
+  c->mirror_copied = c->h_page->mirror_head;
+  return TML_OK;
+}
+
 int tml_drain(tml_ctx* c, tml_step_record* out, uint32_t max_records, uint32_t* n_out,
               uint64_t* n_dropped) {
   if (!c || !out || !n_out) return TML_ERR_ARG;
+  if (c->drain_tail >= c->h_page->mirror_head) {  // nothing left over from the last refresh
+    int rc = refresh_mirror(c);
+    if (rc != TML_OK) return rc;
+  }
   u64 head = c->h_page->mirror_head;
   std::atomic_thread_fence(std::memory_order_acquire);
   u64 tail = c->drain_tail, dropped = 0;
@@ -1700,6 +1739,10 @@ int tml_proc_drain(tml_ctx* c, tml_proc_record* out, uint32_t max_records, uint3
 
 int tml_live(tml_ctx* c, tml_live_stats* out) {
   if (!c || !out) return TML_ERR_ARG;
+  {
+    int rc = refresh_mirror(c);
+    if (rc != TML_OK) return rc;
+  }
   memcpy(out, (const void*)&c->h_page->live, sizeof(tml_live_stats));
   return TML_OK;
 }
@@ -1746,6 +1789,9 @@ int tml_ring_load(tml_ctx* c, const tml_step_record* host, uint64_t n, void* str
   k_set_heads<<<1, 1, 0, s>>>(c->d_state, c->commits, 0, 0);
   CK(cudaPeekAtLastError());
   c->win_ready = false;
+  // bulk-loaded history is not new telemetry: the sampler's cursor starts behind it
+  c->mirror_copied = c->drain_tail = c->commits;
+  c->h_page->mirror_head = c->commits;
   return TML_OK;
 }
 
@@ -1769,7 +1815,7 @@ int tml_ring_reset(tml_ctx* c) {
   CK(cudaMemset(c->d_state, 0, sizeof(DevState)));
   memset(c->h_page, 0, sizeof(HostPage));
   c->commits = 0; c->proc_commits.store(0); c->next_slot = 0;
-  c->drain_tail = 0; c->pdrain_tail = 0;
+  c->drain_tail = 0; c->pdrain_tail = 0; c->mirror_copied = 0;
   memset(c->host_dur, 0, sizeof(c->host_dur));
   memset(c->host_calls, 0, sizeof(c->host_calls));
   c->win_ready = false;
