@@ -138,13 +138,19 @@ class TraceMLRuntime:
     """
 
     def __init__(self, interval_sec: float = 2.0, sinks: Optional[List[Callable]] = None,
-                 sample_process: bool = True, native_process_hz: float = 0.0):
+                 sample_process: bool = True, native_process_hz: float = 0.0,
+                 sample_system: Optional[bool] = None):
         self.interval = max(1e-4, float(interval_sec))
         self.sinks = list(sinks or [])
         self.sample_process = sample_process
         # > 0: the C++ sampler thread (no GIL) commits process samples at this rate and the
         # Python tick only drains; 0: one sample per tick from Python (the reference cadence)
         self.native_process_hz = float(native_process_hz)
+        # host / NVML snapshot: local rank 0 only, like the reference's registry
+        # (runtime/sampler_registry.py:78-105); None = decide from LOCAL_RANK
+        self.sample_system = (int(os.environ.get("LOCAL_RANK", "0") or 0) == 0) if sample_system is None \
+            else bool(sample_system)
+        self._sys = None
         self._native = None
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
@@ -188,11 +194,21 @@ class TraceMLRuntime:
             with torch.cuda.device(eng.device):
                 self._proc.sample(eng)
         out = drain_to_wire(eng, ram_total=getattr(self._proc, "ram_total", None))
+        out["system"] = []
+        if self.sample_system and self.sinks:
+            try:
+                if self._sys is None:
+                    from ..samplers import SystemProbe
+
+                    self._sys = SystemProbe()
+                out["system"] = [self._sys.sample()]
+            except Exception as exc:  # noqa: BLE001
+                print(f"[TraceML] system sample failed: {exc}", file=sys.stderr)
         self.steps_seen += len(out["step_time"])
         self.dropped += out["dropped"]
         self.ticks += 1
         for sink in self.sinks:
-            for kind in ("step_time", "step_memory", "process"):
+            for kind in ("step_time", "step_memory", "process", "system"):
                 if out[kind]:
                     try:
                         sink(kind, out[kind])

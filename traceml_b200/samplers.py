@@ -259,12 +259,109 @@ class ProcessSampler(_TapSampler):
         super().sample()
 
 
-def build_samplers(engine) -> List[_TapSampler]:
+class SystemProbe:
+    """One host / all-GPU snapshot per call: the wire row of ``SystemSample.to_wire``
+    (samplers/system_sampler.py:42-221, samplers/schema/system.py:133-157).  Host-side by nature
+    (psutil + NVML); there is no device-side counterpart, so nothing goes through the ring: the row
+    is handed to the sinks as it is.  NVML failures degrade to CPU/RAM only, a failing GPU yields
+    the reference's zeroed placeholder so that index == GPU id."""
+
+    def __init__(self):
+        import psutil
+
+        self._psutil = psutil
+        self.seq = 0
+        self.cores = 0
+        self.ram_total = 0.0
+        self.gpu_available = False
+        self.gpu_count = 0
+        self._nvml = None
+        try:
+            psutil.cpu_percent(interval=None)  # warm-up: the first real call must not block
+            self.cores = psutil.cpu_count(logical=True) or 0
+            self.ram_total = float(psutil.virtual_memory().total)
+        except Exception:
+            pass
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self.gpu_count = int(pynvml.nvmlDeviceGetCount())
+            self.gpu_available = self.gpu_count > 0
+        except Exception:
+            self._nvml = None
+
+    def _gpus(self) -> List[List[float]]:
+        if not self.gpu_available or self._nvml is None:
+            return []
+        n, out = self._nvml, []
+        for i in range(self.gpu_count):
+            try:
+                h = n.nvmlDeviceGetHandleByIndex(i)
+                util = n.nvmlDeviceGetUtilizationRates(h)
+                mem = n.nvmlDeviceGetMemoryInfo(h)
+                temp = n.nvmlDeviceGetTemperature(h, n.NVML_TEMPERATURE_GPU)
+                out.append([float(util.gpu), float(mem.used), float(mem.total), float(temp),
+                            float(n.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                            float(n.nvmlDeviceGetPowerManagementLimit(h) / 1000.0)])
+            except Exception:
+                out.append([0.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        return out
+
+    def sample(self) -> Dict[str, Any]:
+        self.seq += 1
+        try:
+            cpu = float(self._psutil.cpu_percent(interval=None))
+        except Exception:
+            cpu = 0.0
+        try:
+            ram_used = float(self._psutil.virtual_memory().used)
+        except Exception:
+            ram_used = 0.0
+        return {"seq": self.seq, "ts": time.time(), "cpu": cpu, "ram_used": ram_used,
+                "ram_total": self.ram_total, "gpu_available": self.gpu_available,
+                "gpu_count": self.gpu_count, "gpus": self._gpus()}
+
+
+class SystemSampler:
+    """``BaseSampler`` contract for the host snapshot (runtime/sampler_registry.py:78-105:
+    ``system``, rank-zero only, ``max_rows_per_flush=1``)."""
+
+    sampler_name, table_name, kind = "SystemSampler", "SystemTable", "system"
+
+    def __init__(self, probe: Optional[SystemProbe] = None):
+        self.probe = probe
+        self.db = TableStore(self.sampler_name)
+        self.max_rows_per_flush = 1
+        self.enable_send = True
+        self._last_sent: Dict[str, int] = {}
+
+    def sample(self) -> None:
+        try:
+            if self.probe is None:
+                self.probe = SystemProbe()
+            self.db.add_record(self.table_name, self.probe.sample())
+        except Exception as exc:  # noqa: BLE001
+            import sys
+
+            print(f"[TraceML] SystemSampler.sample failed: {exc}", file=sys.stderr)
+
+    collect_payload = _TapSampler.collect_payload
+
+
+def build_samplers(engine, rank_zero: Optional[bool] = None) -> List[Any]:
     """The per-rank sampler set of profile ``run`` that is on this path
-    (runtime/sampler_registry.py:131-160: process, step_time, step_memory)."""
+    (runtime/sampler_registry.py:78-160: system on local rank 0; process, step_time, step_memory
+    on every rank)."""
     tap = RecordTap(engine)
-    return [ProcessSampler(tap), StepTimeSampler(tap), StepMemorySampler(tap)]
+    out: List[Any] = []
+    if rank_zero is None:
+        rank_zero = int(os.environ.get("LOCAL_RANK", "0") or 0) == 0
+    if rank_zero:
+        out.append(SystemSampler())
+    return out + [ProcessSampler(tap), StepTimeSampler(tap), StepMemorySampler(tap)]
 
 
-__all__ = ["drain_to_wire", "ProcessProbe", "TableStore", "RecordTap", "StepTimeSampler",
-           "StepMemorySampler", "ProcessSampler", "build_samplers"]
+__all__ = ["drain_to_wire", "ProcessProbe", "SystemProbe", "TableStore", "RecordTap", "StepTimeSampler",
+           "StepMemorySampler", "ProcessSampler", "SystemSampler", "build_samplers", "host_constants"]
