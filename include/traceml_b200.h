@@ -592,6 +592,33 @@ typedef struct tml_sections_args {
 int tml_sections_json(const tml_reduce_run_out* run, const tml_sections_args* args,
                       char* json_out, size_t cap);
 
+/* ---------------------------------------------------------------- DEEP PROFILE
+ * K1 / K2 with a layer-id dimension.  Replaces the per-layer CUDA-event pairs,
+ * event objects and queues of instrumentation/hooks/layer_forward_time_hooks.py:113-267,
+ * layer_backward_time_hooks.py:110-264 and the activation sizes of
+ * layer_forward_memory_hooks.py:60-190 / layer_backward_memory_hooks.py; one record per
+ * (step, layer) replaces the four Layer*Sampler aggregations
+ * (samplers/layer_{forward,backward}_{time,memory}_sampler.py).
+ *   tml_layer_init    allocate accumulators + a ring of `steps` x n_layers records
+ *   tml_layer_begin   %globaltimer stamp on `stream` -> slot (shares the 64 begin slots of K1)
+ *   tml_layer_end     stamp + accumulate (t1 - t0), n_calls and the activation bytes of the call
+ *                     into layer `layer`, direction 0 forward / 1 backward
+ *   tml_layer_commit  close the step: snapshot every layer's accumulators into the ring
+ *   tml_layer_drain   completed steps -> host (own stream; never the training stream)        */
+typedef struct tml_layer_record {   /* 48 B per (step, layer) */
+  uint64_t step;
+  uint64_t fwd_ns, bwd_ns;
+  uint32_t fwd_calls, bwd_calls;
+  uint64_t fwd_bytes, bwd_bytes;    /* output activation / grad-output bytes, summed over calls */
+} tml_layer_record;
+
+int tml_layer_init(tml_ctx* ctx, uint32_t n_layers, uint32_t steps);
+int tml_layer_begin(tml_ctx* ctx, void* stream);
+int tml_layer_end(tml_ctx* ctx, uint32_t layer, uint32_t direction, int slot, uint64_t bytes, void* stream);
+int tml_layer_commit(tml_ctx* ctx, uint64_t step, void* stream);
+int tml_layer_drain(tml_ctx* ctx, tml_layer_record* out, uint32_t max_steps, uint32_t* n_steps,
+                    uint32_t* n_layers, uint64_t* n_dropped);
+
 /* ---------------------------------------------------------------- TEST HOOK
  * Host emulation of K3e -- the reference-order window sums (``s += x`` per row:
  * reporting/sections/step_time/model.py:262-268, alignment.py:59-75) computed as composed

@@ -131,6 +131,7 @@ def test_ctypes_mirrors_match_the_c_layouts():
         "tml_rank_means": _abi.RankMeans, "tml_trend_in": _abi.TrendIn, "tml_st_diag_in": _abi.StDiagIn,
         "tml_mem_metric_in": _abi.MemMetricIn, "tml_mem_diag_in": _abi.MemDiagIn,
         "tml_proc_diag_in": _abi.ProcDiagIn, "tml_sections_args": _abi.SectionsArgs,
+        "tml_layer_record": _abi.LayerRecord,
     }
     for name, cls in pairs.items():
         assert int(lib.tml_struct_size(name.encode())) == C.sizeof(cls), name

@@ -39,6 +39,11 @@ class ProcRecord(C.Structure):
                 ("mem_resv", u64), ("mem_total", u64), ("flags", u32), ("cpu_cores", u32)]
 
 
+class LayerRecord(C.Structure):
+    _fields_ = [("step", u64), ("fwd_ns", u64), ("bwd_ns", u64), ("fwd_calls", u32), ("bwd_calls", u32),
+                ("fwd_bytes", u64), ("bwd_bytes", u64)]
+
+
 class LivePhase(C.Structure):
     _fields_ = [("count", u64), ("sum_ns", u64), ("worst_ns", u64), ("median_ns", u64)]
 
@@ -196,6 +201,11 @@ SIGNATURES = {
     "tml_win_fused": (C.c_int, [vp, u32, vp, vp, C.POINTER(WinInfo), C.POINTER(AlignInfo), C.POINTER(u32)]),
     "tml_win_exact_collect": (C.c_int, [vp, vp, C.POINTER(f64)]),
     "tml_win_exact_stats": (C.c_int, [vp, C.POINTER(u64)]),
+    "tml_layer_init": (C.c_int, [vp, u32, u32]),
+    "tml_layer_begin": (C.c_int, [vp, vp]),
+    "tml_layer_end": (C.c_int, [vp, u32, u32, C.c_int, u64, vp]),
+    "tml_layer_commit": (C.c_int, [vp, u64, vp]),
+    "tml_layer_drain": (C.c_int, [vp, vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
     "tml_xs_host_sum": (C.c_int, [vp, u64, C.c_int, C.POINTER(f64), C.POINTER(u64)]),
     "tml_reduce_run": (C.c_int, [vp, C.POINTER(Comm), C.POINTER(ReduceRunArgs), vp, C.POINTER(ReduceRunOut)]),
     "tml_combined_prepare": (C.c_int, [vp, u32, u32, vp, C.POINTER(CombinedInfo)]),

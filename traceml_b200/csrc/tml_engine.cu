@@ -72,6 +72,8 @@ struct DevState {
   u64 live_max[TML_MAX_PHASES];
   u32 hist[TML_N_PHASES][TML_HIST_BINS];
   tml_live_stats live;  // running count / sum / worst / median per phase (k_mirror copies it out)
+  u64 layer_begin_ts[TML_N_SLOTS];  // deep profile: its own begin slots (hundreds of layer regions
+                                    // open and close while ONE phase region stays open)
 };
 
 // host-mapped page: written by kernels, read by the sampler thread with no CUDA call
@@ -292,6 +294,50 @@ __global__ void __launch_bounds__(1024) k_mirror(const DevState* st, const tml_s
   __syncthreads();
   if (threadIdx.x == 0) page->mirror_head = head;
 }
+
+// ------------------------------------------------------------------ K1/K2 with a layer id (deep profile)
+struct LayerAcc {
+  u64 fwd_ns, bwd_ns, fwd_bytes, bwd_bytes;
+  u32 fwd_calls, bwd_calls;
+  u32 _pad[2];
+};
+static_assert(sizeof(LayerAcc) == 48, "LayerAcc");
+
+__global__ void k_layer_begin(DevState* st, u32 slot) {
+  if (threadIdx.x == 0) st->layer_begin_ts[slot] = globaltimer_ns();
+}
+
+__global__ void k_layer_end(DevState* st, LayerAcc* acc, u32 slot, u32 layer, u32 dir, u64 bytes) {
+  if (threadIdx.x == 0) {
+    const u64 t1 = globaltimer_ns();
+    const u64 t0 = st->layer_begin_ts[slot];
+    const u64 d = (t1 > t0) ? (t1 - t0) : 0ull;
+    LayerAcc* a = &acc[layer];
+    if (dir == 0u) { atomicAdd(&a->fwd_ns, d); atomicAdd(&a->fwd_calls, 1u); atomicAdd(&a->fwd_bytes, bytes); }
+    else { atomicAdd(&a->bwd_ns, d); atomicAdd(&a->bwd_calls, 1u); atomicAdd(&a->bwd_bytes, bytes); }
+  }
+}
+
+// one thread per layer: accumulators -> ring slot of this step (48-B records, coalesced), reset
+__global__ void k_layer_commit(LayerAcc* acc, tml_layer_record* ring, u32 n_layers, u32 ring_steps, u64 seq,
+                               u64 step, u64* head) {
+  const u32 l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n_layers) {
+    LayerAcc a = acc[l];
+    tml_layer_record r;
+    r.step = step; r.fwd_ns = a.fwd_ns; r.bwd_ns = a.bwd_ns; r.fwd_calls = a.fwd_calls; r.bwd_calls = a.bwd_calls;
+    r.fwd_bytes = a.fwd_bytes; r.bwd_bytes = a.bwd_bytes;
+    ring[(size_t)(seq % ring_steps) * n_layers + l] = r;
+    LayerAcc z;
+    memset(&z, 0, sizeof(z));
+    acc[l] = z;
+  }
+  __syncthreads();
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) { __threadfence(); *head = seq + 1; }
+  }
+}
+__global__ void k_layer_head(u64* head, u64 v) { *head = v; }
 
 // ------------------------------------------------------------------ K5: proc commit
 
@@ -1420,6 +1466,13 @@ struct tml_ctx {
   void* d_xs_buf = nullptr;      // one allocation, carved into XsWork
   XsWork xs_work;
   double* d_xs_out = nullptr; u64* d_xs_stats = nullptr;
+  // deep profile (layer-id dimension)
+  u32 n_layers = 0, layer_steps = 0, next_layer_slot = 0;
+  LayerAcc* d_layer_acc = nullptr;
+  tml_layer_record* d_layer_ring = nullptr;
+  u64* d_layer_head = nullptr;
+  u64 layer_commits = 0, layer_tail = 0;
+  tml_layer_record* h_layer_stage = nullptr;  // pinned, one step's records
   cudaStream_t xs_stream = nullptr;  // K3e beside K4 (tml_win_set_defer)
   cudaEvent_t xs_gate = nullptr, xs_done = nullptr;
   bool xs_defer = false, xs_pending = false;
@@ -1581,6 +1634,8 @@ int tml_shutdown(tml_ctx* c) {
   cudaFree(c->d_selrow); cudaFree(c->d_selstep); cudaFree(c->d_blockcnt); cudaFree(c->d_total);
   cudaFree(c->d_noncontig); cudaFree(c->d_gacc);
   cudaFree(c->d_xs_buf); cudaFree(c->d_xs_out); cudaFree(c->d_xs_stats);
+  cudaFree(c->d_layer_acc); cudaFree(c->d_layer_ring); cudaFree(c->d_layer_head);
+  if (c->h_layer_stage) cudaFreeHost(c->h_layer_stage);
   if (c->drain_stream) cudaStreamDestroy(c->drain_stream);
   if (c->xs_stream) cudaStreamDestroy(c->xs_stream);
   if (c->xs_gate) cudaEventDestroy(c->xs_gate);
@@ -1636,6 +1691,94 @@ int tml_phase_end(tml_ctx* c, uint32_t phase, int slot, void* stream) {
   c->launches += 1;
   if (cudaPeekAtLastError() != cudaSuccess)
     return set_err(TML_ERR_CUDA, "stamp_end launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return TML_OK;
+}
+
+// ---------------------------------------------------------------- deep profile
+int tml_layer_init(tml_ctx* c, uint32_t n_layers, uint32_t steps) {
+  if (!c || n_layers == 0 || steps == 0) return TML_ERR_ARG;
+  DeviceGuard dg(c);
+  cudaFree(c->d_layer_acc); cudaFree(c->d_layer_ring); cudaFree(c->d_layer_head);
+  if (c->h_layer_stage) cudaFreeHost(c->h_layer_stage);
+  c->d_layer_acc = nullptr; c->d_layer_ring = nullptr; c->d_layer_head = nullptr; c->h_layer_stage = nullptr;
+  CK(cudaMalloc(&c->d_layer_acc, (size_t)n_layers * sizeof(LayerAcc)));
+  CK(cudaMemset(c->d_layer_acc, 0, (size_t)n_layers * sizeof(LayerAcc)));
+  CK(cudaMalloc(&c->d_layer_ring, (size_t)n_layers * steps * sizeof(tml_layer_record)));
+  CK(cudaMalloc(&c->d_layer_head, sizeof(u64)));
+  CK(cudaMemset(c->d_layer_head, 0, sizeof(u64)));
+  CK(cudaHostAlloc(&c->h_layer_stage, ((size_t)n_layers * sizeof(tml_layer_record)) + 64, cudaHostAllocDefault));
+  c->n_layers = n_layers; c->layer_steps = steps; c->layer_commits = 0; c->layer_tail = 0;
+  return TML_OK;
+}
+
+int tml_layer_begin(tml_ctx* c, void* stream) {
+  if (!c || !c->n_layers) return TML_ERR_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);
+  if (check_capture(s)) return TML_ERR_CAPTURE;
+  const u32 slot = c->next_layer_slot;
+  c->next_layer_slot = (slot + 1u) % TML_N_SLOTS;
+  k_layer_begin<<<1, 32, 0, s>>>(c->d_state, slot);
+  c->launches += 1;
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return set_err(TML_ERR_CUDA, "layer_begin launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return (int)slot;
+}
+
+int tml_layer_end(tml_ctx* c, uint32_t layer, uint32_t direction, int slot, uint64_t bytes, void* stream) {
+  if (!c || !c->n_layers || layer >= c->n_layers || direction > 1 || slot < 0 || slot >= (int)TML_N_SLOTS)
+    return TML_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);
+  if (check_capture(s)) return TML_ERR_CAPTURE;
+  k_layer_end<<<1, 32, 0, s>>>(c->d_state, c->d_layer_acc, (u32)slot, layer, direction, bytes);
+  c->launches += 1;
+  if (cudaPeekAtLastError() != cudaSuccess)
+    return set_err(TML_ERR_CUDA, "layer_end launch: %s", cudaGetErrorString(cudaGetLastError()));
+  return TML_OK;
+}
+
+int tml_layer_commit(tml_ctx* c, uint64_t step, void* stream) {
+  if (!c || !c->n_layers) return TML_ERR_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  DeviceGuard dg(c);
+  if (check_capture(s)) return TML_ERR_CAPTURE;
+  const int blocks = (int)((c->n_layers + 255) / 256);
+  k_layer_commit<<<blocks, 256, 0, s>>>(c->d_layer_acc, c->d_layer_ring, c->n_layers, c->layer_steps,
+                                        c->layer_commits, step, c->d_layer_head);
+  if (blocks > 1) k_layer_head<<<1, 1, 0, s>>>(c->d_layer_head, c->layer_commits + 1);
+  CK(cudaPeekAtLastError());
+  c->launches += blocks > 1 ? 2 : 1;
+  c->layer_commits += 1;
+  return TML_OK;
+}
+
+int tml_layer_drain(tml_ctx* c, tml_layer_record* out, uint32_t max_steps, uint32_t* n_steps, uint32_t* n_layers,
+                    uint64_t* n_dropped) {
+  if (!c || !out || !n_steps) return TML_ERR_ARG;
+  *n_steps = 0;
+  if (n_layers) *n_layers = c->n_layers;
+  if (n_dropped) *n_dropped = 0;
+  if (!c->n_layers) return TML_OK;
+  DeviceGuard dg(c);
+  std::lock_guard<std::mutex> g(c->mirror_mu);
+  if (!c->drain_stream) CK(cudaStreamCreateWithFlags(&c->drain_stream, cudaStreamNonBlocking));
+  u64 head = 0;
+  CK(cudaMemcpyAsync(c->h_layer_stage, c->d_layer_head, sizeof(u64), cudaMemcpyDeviceToHost, c->drain_stream));
+  CK(cudaStreamSynchronize(c->drain_stream));
+  memcpy(&head, c->h_layer_stage, sizeof(u64));
+  u64 tail = c->layer_tail;
+  if (head - tail > c->layer_steps) { if (n_dropped) *n_dropped = head - tail - c->layer_steps; tail = head - c->layer_steps; }
+  u32 n = 0;
+  const size_t row = (size_t)c->n_layers * sizeof(tml_layer_record);
+  while (tail < head && n < max_steps) {
+    CK(cudaMemcpyAsync(out + (size_t)n * c->n_layers, c->d_layer_ring + (size_t)(tail % c->layer_steps) * c->n_layers,
+                       row, cudaMemcpyDeviceToHost, c->drain_stream));
+    ++n; ++tail;
+  }
+  CK(cudaStreamSynchronize(c->drain_stream));
+  c->layer_tail = tail;
+  *n_steps = n;
   return TML_OK;
 }
 

@@ -141,6 +141,9 @@ class trace_step:
                 if rc < 0:
                     _timing._ENG.step_discard()
                     print(f"[TraceML] step {_STATE.step} not committed (status {rc})", file=sys.stderr)
+                _layers = sys.modules.get("traceml_b200.instrumentation.layers")
+                if _layers is not None and _layers._PROFILES:  # deep profile: per-layer step close
+                    _layers.commit_all(_STATE.step)
             except Exception as e:
                 _log("flush failed", e)
             return False
@@ -161,12 +164,29 @@ class trace_step:
         return False
 
 
-def trace_model_instance(model, **kwargs) -> None:
-    """Deep (per-layer) profile hooks: out of the hot-path scope (SURVEY section 2);
-    accepted and ignored unless TRACEML_PROFILE=deep, where it reports that."""
+def trace_model_instance(model, sample_layer_memory: bool = True, trace_layer_forward_memory: bool = True,
+                         trace_layer_backward_memory: bool = True, trace_layer_forward_time: bool = True,
+                         trace_layer_backward_time: bool = True, trace_execution: bool = True,
+                         include_names=None, exclude_names=None, leaf_only: bool = True) -> None:
+    """Deep (per-layer) profile: forward / backward device timers and activation sizes per leaf
+    module, same signature and gate as ``sdk/instrumentation.py:203-260`` (``TRACEML_PROFILE=deep``;
+    a no-op otherwise).  K1 / K2 with a layer id: ``instrumentation/layers.py``."""
     if disabled() or (os.environ.get("TRACEML_PROFILE", "run") or "run").strip().lower() != "deep":
         return
-    print("[TraceML] deep (per-layer) profile is not part of the B200 engine", file=sys.stderr)
+    try:
+        import torch.nn as nn
+
+        if not isinstance(model, nn.Module):
+            raise TypeError("trace_model_instance expects an nn.Module.")
+        from ..instrumentation import layers
+        from ..runtime import get_engine
+
+        layers.attach(get_engine(), model, include_names=include_names, exclude_names=exclude_names,
+                      leaf_only=leaf_only,
+                      forward=bool(trace_layer_forward_time or trace_layer_forward_memory),
+                      backward=bool(trace_layer_backward_time or trace_layer_backward_memory))
+    except Exception as exc:  # noqa: BLE001 -- never into user code
+        _log("trace_model_instance failed", exc)
 
 
 def trace_time(name: str, scope: str = "global", use_gpu: bool = True) -> Callable:

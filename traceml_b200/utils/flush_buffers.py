@@ -31,6 +31,9 @@ def flush_step_events(model, step: int) -> None:
         if rc < 0:
             eng.step_discard()
             print(f"[TraceML] step {step} not committed (status {rc})", file=sys.stderr)
+        _layers = sys.modules.get("traceml_b200.instrumentation.layers")
+        if _layers is not None and _layers._PROFILES:  # deep profile: close the step for every layer too
+            _layers.commit_all(int(step))
     except timing._Quiet:
         pass  # engine resolution failed and was reported once
     except Exception as exc:
