@@ -36,6 +36,8 @@ def load_golden(name: str) -> Dict[str, Any]:
 
 
 def plain(obj):
+    if hasattr(obj, "to_dict") and not isinstance(obj, dict):  # traceml_b200._abi.Sections (lazy view)
+        obj = obj.to_dict()
     if isinstance(obj, dict):
         return {str(k): plain(v) for k, v in obj.items()}
     if isinstance(obj, (list, tuple)):

@@ -151,6 +151,8 @@ def test_layer_times_next_to_the_reference_hooks(deep):
         for i, name in enumerate(prof.names):
             mine = float(row["fwd_ns"][i]) / 1000.0
             assert mine >= by_name[name] - (2.0 + 0.01 * mine), (name, mine, by_name[name])
-            assert mine <= by_name[name] + 40.0, (name, mine, by_name[name])
+            # ours is the OUTER pair: the reference's own hook work (two event records, Python)
+            # sits between our stamps and shows up as device idle time on this tiny model
+            assert mine <= by_name[name] + 150.0, (name, mine, by_name[name])
     prof.detach()
     eng.close()

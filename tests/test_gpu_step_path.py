@@ -126,6 +126,7 @@ def test_trace_step_public_api(cuda):
     traceml.init(mode="auto")
     eng = runtime.get_engine()
     eng.drain()
+    eng.step_discard()   # a previous test's exhausted DataLoader left its last fetch pending (as the reference would)
     model = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.ReLU(), torch.nn.Linear(512, 10)).cuda()
     opt = torch.optim.SGD(model.parameters(), lr=0.01)
     ds = torch.utils.data.TensorDataset(torch.randn(64 * 6, 256), torch.randint(0, 10, (64 * 6,)))

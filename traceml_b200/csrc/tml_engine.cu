@@ -92,6 +92,7 @@ struct CommitArgs {
   u32 flags;
   u64 peak_alloc;  // c10 allocator peaks of the step (host state: they travel as launch arguments)
   u64 peak_resv;
+  u64 seq;         // commit number = ring position (the host counts them)
 };
 
 struct WinAcc {  // integer side results of k_window_rows (atomics; order-independent)
@@ -173,11 +174,21 @@ __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   DevAcc* acc = &st->acc[a.epoch];
 
-  u64 dur = 0;
+  // ONE global round trip on the critical path: the phase accumulator and the 256-bin histogram
+  // (8 bins per lane) are fetched together; the +1 of this step is applied in registers and
+  // written back without being waited for.  (r01: accumulator -> histogram RMW -> histogram
+  // re-read -> head read, four dependent round trips, 5.3-7.6 us.)
+  u32* h = st->hist[warp];
+  u32 c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k] = h[lane * 8 + k];
+  u64 dur = 0, run_sum = 0, run_max = 0;
   u32 calls = 0;
   if (lane == 0) {
     dur = acc->dur_ns[warp] + a.host_dur[warp];
     calls = acc->n_calls[warp] + a.host_calls[warp];
+    run_sum = st->live_sum[warp];
+    run_max = st->live_max[warp];
     s_dur[warp] = dur;
     s_calls[warp] = calls;
     acc->dur_ns[warp] = 0;
@@ -195,13 +206,17 @@ __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* r
   // running statistics of phase `warp`: count / sum / worst exactly, median from
   // the log histogram by a warp-shuffle inclusive scan of per-lane bin counts.
   if (calls > 0u) {
-    u32* h = st->hist[warp];
-    if (lane == 0) h[hist_bin(dur)] += 1u;
-    __syncwarp();
-    u32 c[8];
+    const u32 bin = hist_bin(dur);
+    if ((int)(bin >> 3) == lane) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c[k] += ((bin & 7u) == (u32)k) ? 1u : 0u;
+      h[bin] = c[0] * ((bin & 7u) == 0u) + c[1] * ((bin & 7u) == 1u) + c[2] * ((bin & 7u) == 2u) +
+               c[3] * ((bin & 7u) == 3u) + c[4] * ((bin & 7u) == 4u) + c[5] * ((bin & 7u) == 5u) +
+               c[6] * ((bin & 7u) == 6u) + c[7] * ((bin & 7u) == 7u);
+    }
     u32 local = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; local += c[k]; }
+    for (int k = 0; k < 8; ++k) local += c[k];
     u32 incl = local;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -213,49 +228,44 @@ __global__ void __launch_bounds__(192) k_commit(DevState* st, tml_step_record* r
     u32 excl = incl - local;
     unsigned hit = __ballot_sync(0xffffffffu, (excl < target) && (target <= incl));
     int src = __ffs(hit) - 1;
-    u64 med = 0;
+    const u64 sum = __shfl_sync(0xffffffffu, run_sum, 0) + dur;
+    u64 mx = __shfl_sync(0xffffffffu, run_max, 0);
+    mx = dur > mx ? dur : mx;
     if (lane == src) {
       u32 run = excl;
-      u32 bin = lane * 8;
+      u32 mbin = lane * 8;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         run += c[k];
-        if (run >= target) { bin = lane * 8 + k; break; }
+        if (run >= target) { mbin = lane * 8 + k; break; }
       }
-      med = hist_bin_center(bin);
-      u64 sum = st->live_sum[warp] + dur;
-      u64 mx = st->live_max[warp];
-      mx = dur > mx ? dur : mx;
       st->live_sum[warp] = sum;
       st->live_max[warp] = mx;
       tml_live_phase* lp = &st->live.phase[warp];
       lp->count = total;
       lp->sum_ns = sum;
       lp->worst_ns = mx;
-      lp->median_ns = med;
+      lp->median_ns = hist_bin_center(mbin);
     }
   }
   __syncthreads();
 
   if (warp == 0) {
-    u64 seq = 0;
+    const u64 seq = a.seq;  // the host counts commits: no read of the head on the critical path
     if (lane == 0) {
-      seq = st->head;
-      const u64 peak_alloc = a.peak_alloc, peak_resv = a.peak_resv;
       rec[0] = a.step;
 #pragma unroll
       for (int p = 0; p < 6; ++p) rec[1 + p] = s_dur[p];
       rec[7] = (u64)s_calls[0] | ((u64)s_calls[1] << 32);
       rec[8] = (u64)s_calls[2] | ((u64)s_calls[3] << 32);
       rec[9] = (u64)s_calls[4] | ((u64)s_calls[5] << 32);
-      rec[10] = peak_alloc;
-      rec[11] = peak_resv;
+      rec[10] = a.peak_alloc;
+      rec[11] = a.peak_resv;
       rec[12] = (u64)__double_as_longlong(a.host_ts);
       rec[13] = (u64)s_mask | ((u64)a.flags << 32);
       rec[14] = seq;
       rec[15] = 0;
     }
-    seq = __shfl_sync(0xffffffffu, seq, 0);
     __syncwarp();
     if (lane < 8) {
       uint4 v = reinterpret_cast<const uint4*>(rec)[lane];
@@ -1810,6 +1820,7 @@ int tml_step_commit(tml_ctx* c, uint64_t step, uint64_t peak_alloc, uint64_t pea
   a.flags = flags;
   a.peak_alloc = peak_alloc;
   a.peak_resv = peak_resv;
+  a.seq = c->commits;
   k_commit<<<1, 192, 0, s>>>(c->d_state, c->d_ring, c->ring_slots, a);
   memset(c->host_dur, 0, sizeof(c->host_dur));
   memset(c->host_calls, 0, sizeof(c->host_calls));
