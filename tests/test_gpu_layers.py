@@ -127,8 +127,8 @@ def test_layer_times_next_to_the_reference_hooks(deep):
 
     eng = Engine(device=0, ring_slots=64)
     model = _model()
-    prof = deep.LayerProfile(eng, model, backward=False)   # our hooks first: outer pair
-    attach_layer_forward_time_hooks(model)                 # the reference's: inner pair
+    attach_layer_forward_time_hooks(model)                                  # the reference's: inner pair
+    prof = deep.LayerProfile(eng, model, backward=False, outermost=True)     # ours brackets them
     x = torch.randn(512, 1024, device="cuda")
     n = 30
     for step in range(1, n + 1):

@@ -49,7 +49,7 @@ recs, dropped = eng.drain()
 assert dropped == 0 and list(recs["step"]) == [1, 2, 3, 4, 5], list(recs["step"])   # its step counter
 assert (recs["n_calls"][:, 0] == 1).all(), recs["n_calls"][:, 0]      # dataloader_next (its patch)
 assert (recs["n_calls"][:, 1] == 2).all(), recs["n_calls"][:, 1]      # two H2D copies (its patch)
-assert (recs["n_calls"][:, 2:6] == 1).all() and (recs["dur_ns"][:, 2:6] > 0).all()
+assert (recs["n_calls"][:, 2:6] == 1).all() and (recs["dur_ns"][:, 2:6] > 0).all(), (recs["n_calls"], recs["dur_ns"])
 assert (recs["gpu_mask"] == 0b011110).all()                            # device-stamped phases
 assert [int(v) for v in recs["peak_alloc"]] == expect                  # a5 through the shim
 from traceml.samplers.step_time_sampler import StepTimeSampler       # rebound to the ring drain

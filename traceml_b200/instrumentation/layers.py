@@ -63,7 +63,10 @@ class LayerProfile:
     """Hooks + drain for one model on one engine."""
 
     def __init__(self, engine, model: nn.Module, include_names=None, exclude_names=None, leaf_only: bool = True,
-                 ring_steps: int = 256, forward: bool = True, backward: bool = True):
+                 ring_steps: int = 256, forward: bool = True, backward: bool = True, outermost: bool = False):
+        """``outermost``: open the region before any hook registered earlier on the same module
+        (pre-hooks are prepended); the closing hooks are appended, so with hooks attached LAST
+        this profile brackets every other hook's work."""
         self.engine = engine
         self.model_id = id(model)
         self.names: List[str] = []
@@ -100,10 +103,10 @@ class LayerProfile:
                         end(h, _lid, 1, slot, _tensor_bytes(gout), raw_stream(dev))
 
             if forward:
-                self.handles.append(m.register_forward_pre_hook(pre))
+                self.handles.append(m.register_forward_pre_hook(pre, prepend=outermost))
                 self.handles.append(m.register_forward_hook(post))
             if backward:
-                self.handles.append(m.register_full_backward_pre_hook(bpre))
+                self.handles.append(m.register_full_backward_pre_hook(bpre, prepend=outermost))
                 self.handles.append(m.register_full_backward_hook(bpost))
         self._buf = np.zeros((8, len(mods)), dtype=LAYER_RECORD_DTYPE)
         self.seq = 0

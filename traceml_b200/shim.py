@@ -17,6 +17,7 @@ What is rebound (SURVEY 8b "instrumentation seam"; reference file:line):
     utils/step_memory.py:30 StepMemoryTracker       -> ... StepMemoryTracker (c10 peaks, no dict)
     utils/step_memory.py:93 flush_step_memory_buffer-> no-op
     utils/flush_buffers.py:24 flush_step_events     -> ... flush_step_events (tml_step_commit)
+    hooks/optimizer_hooks.py:17 install_optimizer_time_hooks -> instrumentation.patches.* (stamps)
     samplers/{step_time,step_memory,process}_sampler -> traceml_b200.samplers.* (drain of the ring)
 The reference binds these names with ``from ... import name``, so every already-imported
 ``traceml.*`` module that holds one of them is patched in place; modules imported later pick the
@@ -43,10 +44,15 @@ _SEAM = {
     "StepMemoryTracker": "traceml.utils.step_memory",
     "flush_step_memory_buffer": "traceml.utils.step_memory",
     "flush_step_events": "traceml.utils.flush_buffers",
+    # the optimizer hooks open their region by hand (two pooled CUDA events + a TimeEvent,
+    # hooks/optimizer_hooks.py:17-92): rebind the installer, the hooks become stamp kernels
+    "install_optimizer_time_hooks": "traceml.instrumentation.hooks.optimizer_hooks",
+    "ensure_optimizer_timing_installed": "traceml.instrumentation.hooks.optimizer_hooks",
 }
 
 
 def _replacements() -> Dict[str, Any]:
+    from .instrumentation import patches as pt
     from .utils import flush_buffers as fb
     from .utils import step_memory as sm
     from .utils import timing as tm
@@ -61,6 +67,8 @@ def _replacements() -> Dict[str, Any]:
         "StepMemoryTracker": sm.StepMemoryTracker,
         "flush_step_memory_buffer": _noop_flush_memory,
         "flush_step_events": fb.flush_step_events,
+        "install_optimizer_time_hooks": pt.install_optimizer_time_hooks,
+        "ensure_optimizer_timing_installed": pt.ensure_optimizer_timing_installed,
     }
 
 
