@@ -82,6 +82,23 @@ def test_reference_consumers_read_device_fed_database(tmp_path):
     ref_payload = generate_summary(db, session_root=str(root), print_to_stdout=False)
     assert (root / "final_summary.json").exists() and ref_payload["step_time"]["diagnosis"]["status"]
     assert ref_payload["system"] and ref_payload["system"].get("metadata") is not None   # f3 rows reached the System card
+    # structural diff of the two final_summary documents: same keys, section by section, all the way down
+    def tree(x):
+        if isinstance(x, dict):
+            return {k: tree(v) for k, v in sorted(x.items())}
+        if isinstance(x, list):
+            return [tree(x[0])] if x else []
+        return type(x).__name__ if x is not None else "None"
+
+    mine_p = plain(mine)
+    for sec in ("step_time", "step_memory", "process"):
+        a, b = tree(mine_p[sec]), tree(plain(ref_payload[sec]))
+        for k in ("metadata", "diagnosis", "global", "groups", "units"):
+            ak, bk = a.get(k), b.get(k)
+            if isinstance(ak, dict) and isinstance(bk, dict):
+                assert set(ak) == set(bk), (sec, k, sorted(set(ak) ^ set(bk)))
+        assert set(a) == set(b), (sec, sorted(set(a) ^ set(b)))
+    assert {"schema_version", "generated_at", "duration_s", "system", "process", "step_time", "step_memory", "text"} <= set(mine_p)
     ours_json = tmp_path / "ours_final_summary.json"
     ours_json.write_text(json.dumps(plain(mine)))
     cmp_payload = compare_summaries(root / "final_summary.json", ours_json, output=str(tmp_path / "cmp"),

@@ -2056,7 +2056,9 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
     // beside the row exchange / K4: side stream, gated on K3a; the tree sums stand in until
     // tml_win_exact_collect
     if (!c->xs_stream) {
-      CK(cudaStreamCreateWithFlags(&c->xs_stream, cudaStreamNonBlocking));
+      int prio_lo = 0, prio_hi = 0;  // highest priority: K3e's CTAs are placed before K4's when slots free up
+      CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CK(cudaStreamCreateWithPriority(&c->xs_stream, cudaStreamNonBlocking, prio_hi));
       CK(cudaEventCreateWithFlags(&c->xs_gate, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&c->xs_done, cudaEventDisableTiming));
     }
@@ -2495,9 +2497,13 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
   p.series = a->series; p.n_common = a->n_common;
   p.shard_lo = a->shard_lo; p.shard_hi = a->shard_hi;
   p.mask = a->mask; p.n_ranks = a->n_ranks;
-  // 32 regs x 256 threads: 8 CTAs/SM resident; a multiple of the SM count, grid-stride inside
+  // 32 regs x 256 threads: 8 CTAs/SM could be resident; a multiple of the SM count, grid-stride
+  // inside.  With several ranks the kernel is NVLink-bound -- 4 CTAs/SM already keep 16 x the
+  // bandwidth-delay product in flight -- and the other half of every SM is left to K3e, which
+  // runs beside it on the side stream (r02 N = 8 before this: the persistent K4 CTAs held every
+  // slot, K3e's later kernels queued behind them and the two ran back to back: 0.37 + 0.30 ms).
   u64 need = ((a->shard_hi - a->shard_lo) * 4 + RD_THREADS - 1) / RD_THREADS;
-  const u64 cap = (u64)c->n_sms * 8ull;
+  const u64 cap = (u64)c->n_sms * (a->n_ranks > 1 ? 4ull : 8ull);
   const int grid = (int)(need < cap ? (need ? need : 1) : cap);
   if (!c->ev2) { CK(cudaEventCreate(&c->ev2)); CK(cudaEventCreate(&c->ev3)); }
   CK(cudaEventRecord(c->ev2, s));
