@@ -488,7 +488,7 @@ __device__ __forceinline__ void wr_issue_warp(uint4* buf, const uint4* __restric
 __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     const tml_step_record* __restrict__ ring, u32 ring_slots, u64 first_k, u64 n, u64 t_start,
     tml_window_row* __restrict__ rows, u64* __restrict__ steps, u8* __restrict__ flags,
-    WinAcc* acc, double* partials) {
+    WinAcc* acc, double* partials, double* __restrict__ csum, u64 csum_top) {
   extern __shared__ __align__(16) unsigned char wr_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint4* w_in0 = reinterpret_cast<uint4*>(wr_smem) + warp * WR_WARP_U4;
@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     u32 next_flags = __shfl_down_sync(0xffffffffu, rflags, 1);
     if (lane == 0) prev_step = halo_step;
     if (lane == 31) { next_step = halo_step; next_flags = halo_flags; }
+    double t_dl = 0.0, t_fwd = 0.0, t_bwd = 0.0, t_opt = 0.0, t_wall = 0.0, t_tr = 0.0;  // K3e chunk sums
 
     if (live) {
       const u64 d0 = (u64)c0.z | ((u64)c0.w << 32);
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       const bool has_mem = (rflags & TML_REC_HAS_MEM) != 0u;
       const bool usable = (dl > 0.0) || (fwd > 0.0) || (bwd > 0.0) || (opt > 0.0) || (wall > 0.0);
       const bool in_time = i >= t_start;
+      const bool uit = usable && in_time;
       const bool has_prev = i > 0, has_next = (i + 1) < n;
       const bool first_in_win = (i == t_start) || !has_prev || (prev_step != step);
       const bool last_m = !has_next || (next_step != step) || ((next_flags & TML_REC_HAS_MEM) == 0u);
@@ -599,6 +601,9 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
         mx_a = fmax(mx_a, (double)pa); mx_r = fmax(mx_r, (double)pr);
       }
 
+      if (csum) { t_dl = uit ? dl : 0.0; t_fwd = uit ? fwd : 0.0; t_bwd = uit ? bwd : 0.0; t_opt = uit ? opt : 0.0;
+                  t_wall = uit ? wall : 0.0; t_tr = uit ? fmax(wall, (fwd + bwd) + opt) : 0.0; }
+
       // row -> swizzled staging (4 x 16 B)
       double2 o0 = make_double2(dl, h2d), o1 = make_double2(fwd, bwd);
       double2 o2 = make_double2(opt, wall), o3 = make_double2((double)pa, (double)pr);
@@ -607,6 +612,24 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       w_out[lane * 4 + (1 ^ so)] = *reinterpret_cast<uint4*>(&o1);
       w_out[lane * 4 + (2 ^ so)] = *reinterpret_cast<uint4*>(&o2);
       w_out[lane * 4 + (3 ^ so)] = *reinterpret_cast<uint4*>(&o3);
+    }
+    if (csum) {
+      // approximate sums of this 32-row tile for K3e's plan (any order will do: they only choose the
+      // exponent a chunk is composed under, and that choice is verified): warp tree + 7 atomics.
+      // The tile lies inside ONE 256-row chunk because chunks are aligned to row indices
+      double v6 = t_dl + t_tr;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        t_dl += shfl_xor_f64(t_dl, m); t_fwd += shfl_xor_f64(t_fwd, m); t_bwd += shfl_xor_f64(t_bwd, m);
+        t_opt += shfl_xor_f64(t_opt, m); t_wall += shfl_xor_f64(t_wall, m); t_tr += shfl_xor_f64(t_tr, m);
+        v6 += shfl_xor_f64(v6, m);
+      }
+      if (base <= csum_top) {
+        double* dst = csum + ((csum_top - base) >> 8) * 8;
+        const double v = lane == 0 ? t_dl : lane == 1 ? t_fwd : lane == 2 ? t_bwd : lane == 3 ? t_opt
+                       : lane == 4 ? t_wall : lane == 5 ? t_tr : v6;
+        if (lane < 7 && v != 0.0) atomicAdd(dst + lane, v);
+      }
     }
     __syncwarp();
     if (base + 32 <= n) {
@@ -1505,46 +1528,54 @@ static int grid_for(const tml_ctx* c, u64 work_items, int per_block) {
   return (int)(need < cap ? need : cap);
 }
 
+// K3e workspace for `nchunks` chunks (one allocation, carved into XsWork)
+static int xs_ensure(tml_ctx* c, long long nchunks) {
+  if ((u64)nchunks <= c->cap_xs && c->d_xs_buf) return TML_OK;
+  cudaFree(c->d_xs_buf);
+  c->d_xs_buf = nullptr; c->cap_xs = 0;
+  const u64 cap = (u64)nchunks + (u64)nchunks / 4 + 64, gcap = (cap + XS_GROUP - 1) / XS_GROUP + 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_csum = take(cap * 8 * sizeof(double)), o_cpre = take(cap * 8 * sizeof(double));
+  const size_t nb_cap = (size_t)((cap + XS_WARPS - 1) / XS_WARPS + 1);
+  const size_t o_btot = take(nb_cap * 8 * sizeof(double)), o_bpre = take(nb_cap * 8 * sizeof(double));
+  const size_t o_plan = take(cap * 8 * sizeof(int)), o_ea = take(cap * 8 * sizeof(int));
+  const size_t o_fn = take(cap * 7 * sizeof(XsFn)), o_gfn = take(gcap * 7 * sizeof(XsFn));
+  const size_t o_gplan = take(gcap * 8 * sizeof(int)), o_tiles = take((size_t)XS_SLOT_CAP * sizeof(XsTileMaps));
+  const size_t o_ns = take(256);
+  CK(cudaMalloc(&c->d_xs_buf, off));
+  char* base = (char*)c->d_xs_buf;
+  XsWork w;
+  w.csum = (double*)(base + o_csum); w.cpre = (double*)(base + o_cpre);
+  w.btot = (double*)(base + o_btot); w.bpre = (double*)(base + o_bpre);
+  w.plan = (int*)(base + o_plan); w.ea = (int*)(base + o_ea);
+  w.fn = (XsFn*)(base + o_fn); w.gfn = (XsFn*)(base + o_gfn); w.gplan = (int*)(base + o_gplan);
+  w.tiles = (XsTileMaps*)(base + o_tiles); w.nslots = (unsigned int*)(base + o_ns);
+  c->xs_work = w;
+  c->cap_xs = cap;
+  return TML_OK;
+}
+
 // K3e launcher: the seven sums of `src` in reference order -> d_out[0..7) (device), on stream s.
-static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaStream_t s) {
-  const long long n = src.last - src.first + 1;
+// have_csum: the approximate chunk sums are already in the workspace (K3a put them there).
+static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaStream_t s, bool have_csum = false) {
+  const long long n = src.last - src.first + 1 + src.pad;  // summation positions, leading pad included
   // one workspace per context: a job on another stream must wait for the deferred one
   if (c->xs_pending && s != c->xs_stream) CK(cudaStreamWaitEvent(s, c->xs_done, 0));
-  if (n <= 0) { CK(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), s)); return TML_OK; }
+  if (n - src.pad <= 0) { CK(cudaMemsetAsync(d_out, 0, 7 * sizeof(double), s)); return TML_OK; }
   const long long nchunks = (n + XS_CHUNK - 1) / XS_CHUNK, ngroups = (nchunks + XS_GROUP - 1) / XS_GROUP;
   const int planned = n > 1024 ? 1 : 0;  // tiny windows: the walk adds / composes every tile itself
-  // one trip of 8 chunks per CTA: the chunks that cross a binade (slow path of X3) cluster at the
-  // head of the sum and must not queue up behind each other inside one CTA
   const long long max_grid = (long long)c->n_sms * 8;
-  if ((u64)nchunks > c->cap_xs || !c->d_xs_buf) {
-    cudaFree(c->d_xs_buf);
-    c->d_xs_buf = nullptr; c->cap_xs = 0;
-    const u64 cap = (u64)nchunks + (u64)nchunks / 4 + 64, gcap = (cap + XS_GROUP - 1) / XS_GROUP + 1;
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_csum = take(cap * 8 * sizeof(double)), o_cpre = take(cap * 8 * sizeof(double));
-    const size_t nb_cap = (size_t)((cap + XS_WARPS - 1) / XS_WARPS + 1);
-    const size_t o_btot = take(nb_cap * 8 * sizeof(double)), o_bpre = take(nb_cap * 8 * sizeof(double));
-    const size_t o_plan = take(cap * 8 * sizeof(int)), o_ea = take(cap * 8 * sizeof(int));
-    const size_t o_fn = take(cap * 7 * sizeof(XsFn)), o_gfn = take(gcap * 7 * sizeof(XsFn));
-    const size_t o_gplan = take(gcap * 8 * sizeof(int)), o_tiles = take((size_t)XS_SLOT_CAP * sizeof(XsTileMaps));
-    const size_t o_ns = take(256);
-    CK(cudaMalloc(&c->d_xs_buf, off));
-    char* base = (char*)c->d_xs_buf;
-    XsWork w;
-    w.csum = (double*)(base + o_csum); w.cpre = (double*)(base + o_cpre);
-    w.btot = (double*)(base + o_btot); w.bpre = (double*)(base + o_bpre);
-    w.plan = (int*)(base + o_plan); w.ea = (int*)(base + o_ea);
-    w.fn = (XsFn*)(base + o_fn); w.gfn = (XsFn*)(base + o_gfn); w.gplan = (int*)(base + o_gplan);
-    w.tiles = (XsTileMaps*)(base + o_tiles); w.nslots = (unsigned int*)(base + o_ns);
-    c->xs_work = w;
-    c->cap_xs = cap;
+  {
+    int rc = xs_ensure(c, nchunks);
+    if (rc != TML_OK) return rc;
   }
   const XsWork& w = c->xs_work;
   if (planned) {
     const long long want = (nchunks + XS_WARPS - 1) / XS_WARPS;
     const int grid = (int)(want < max_grid ? want : max_grid);
-    k_xs_partial<<<grid, XS_WARPS * 32, 0, s>>>(src, n, nchunks, w);
+    if (have_csum) k_xs_prefix<<<grid, 32, 0, s>>>(nchunks, w);
+    else k_xs_partial<<<grid, XS_WARPS * 32, 0, s>>>(src, n, nchunks, w);
     CK(cudaPeekAtLastError());
     k_xs_bscan<<<1, 1024, 0, s>>>(w, grid);
     CK(cudaPeekAtLastError());
@@ -1569,6 +1600,7 @@ static XsSrc xs_window_src(const tml_ctx* c, long long first, long long last) {
   memset(&x, 0, sizeof(x));
   x.rows = c->d_rows; x.flags = c->d_flags; x.need = RF_USABLE | RF_IN_TIME;
   x.first = first; x.last = last; x.aligned = 0; x.dense_first = -1;
+  x.pad = (XS_CHUNK - ((last + 1) % XS_CHUNK)) % XS_CHUNK;  // chunk boundaries on row indices: see XsSrc::pad
   return x;
 }
 
@@ -2042,16 +2074,30 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   int grid = (int)((n + WR_THREADS - 1) / WR_THREADS);
   if (grid > c->n_sms * 2) grid = c->n_sms * 2;  // 2 resident CTAs per SM (83 KB smem each)
   if (!c->ev0) { CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); }
+  // K3e (reference-order sums) needs approximate 256-row chunk sums for its plan: K3a has every row
+  // in registers anyway and adds them up on the way (tml_exact_sum.cuh: X1 without a pass of its own)
+  bool exact_win = c->world > 1 || (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
+  const XsSrc wsrc = xs_window_src(c, (long long)c->win_tstart, (long long)n - 1);
+  const long long w_pos = (long long)(n - c->win_tstart) + wsrc.pad;
+  const bool k3a_csum = exact_win && w_pos > 1024;
+  double* d_csum = nullptr;
+  if (k3a_csum) {
+    if (c->xs_pending) { CK(cudaStreamWaitEvent(s, c->xs_done, 0)); c->xs_pending = false; }
+    const long long nchunks = (w_pos + XS_CHUNK - 1) / XS_CHUNK;
+    int xr = xs_ensure(c, nchunks);
+    if (xr != TML_OK) return xr;
+    d_csum = c->xs_work.csum;
+    CK(cudaMemsetAsync(d_csum, 0, (size_t)nchunks * 8 * sizeof(double), s));
+  }
   CK(cudaEventRecord(c->ev0, s));
   k_window_rows<<<grid, WR_THREADS, WR_SMEM_BYTES, s>>>(c->d_ring, c->ring_slots, first_k, n, c->win_tstart,
                                             c->d_rows, c->d_steps, c->d_flags, c->d_winacc,
-                                            c->d_partials);
+                                            c->d_partials, d_csum, (u64)(n - 1 + wsrc.pad));
   CK(cudaPeekAtLastError());
   CK(cudaEventRecord(c->ev1, s));
   k_finalize<<<1, 32 * 11, 0, s>>>(c->d_partials, grid, 11, (1u << 9) | (1u << 10), c->d_final + 32);
   CK(cudaPeekAtLastError());
   c->launches += 2;  // K3a + its finalize
-  bool exact_win = c->world > 1 || (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
   if (exact_win && c->xs_defer) {
     // beside the row exchange / K4: side stream, gated on K3a; the tree sums stand in until
     // tml_win_exact_collect
@@ -2064,14 +2110,13 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
     }
     CK(cudaEventRecord(c->xs_gate, s));
     CK(cudaStreamWaitEvent(c->xs_stream, c->xs_gate, 0));
-    int xr = launch_exact_sums(c, xs_window_src(c, (long long)c->win_tstart, (long long)n - 1), c->d_xs_out,
-                               c->xs_stream);
+    int xr = launch_exact_sums(c, wsrc, c->d_xs_out, c->xs_stream, k3a_csum);
     if (xr != TML_OK) return xr;
     CK(cudaEventRecord(c->xs_done, c->xs_stream));
     c->xs_pending = true;
     exact_win = false;
   } else if (exact_win) {  // reference-order sums (used instead of the tree sums)
-    int xr = launch_exact_sums(c, xs_window_src(c, (long long)c->win_tstart, (long long)n - 1), c->d_final, s);
+    int xr = launch_exact_sums(c, wsrc, c->d_final, s, k3a_csum);
     if (xr != TML_OK) return xr;
   }
   // d_final[0..7) exact sums | d_final[32..43) tree sums + maxima | d_final[64..] WinAcc: one copy

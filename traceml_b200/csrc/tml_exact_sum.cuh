@@ -36,6 +36,10 @@ struct XsSrc {
   const u32* noncontig;
   const u32* sel_rows;
   long long dense_first;
+  long long pad;          // leading virtual +0.0 positions: summation position p reads row last - (p - pad).
+                          // Window mode pads so that chunk boundaries fall on row indices that are
+                          // multiples of 256 -- then K3a's 32-row tiles never straddle a chunk and K3a
+                          // itself can deliver the approximate chunk sums (no separate pass over the rows)
 };
 
 struct XsTileMaps {  // one unsafe (chunk, chain): tile maps under exponent ea (h = 0) and ea + 1 (h = 1)
@@ -69,7 +73,8 @@ __device__ __forceinline__ void xs_addends(const tml_window_row* __restrict__ ro
                                            long long n, double (&o)[7]) {
 #pragma unroll
   for (int k = 0; k < 7; ++k) o[k] = 0.0;
-  if (p >= n) return;
+  p -= s.pad;
+  if (p < 0 || p >= n - s.pad) return;
   const long long i = s.last - p;
   if (s.flags && ((s.flags[i] & s.need) != s.need)) return;
   const uint4* src = reinterpret_cast<const uint4*>(rows + i);
@@ -171,6 +176,22 @@ __global__ void __launch_bounds__(XS_WARPS * 32) k_xs_partial(const XsSrc s, lon
     __syncthreads();
   }
   if (threadIdx.x < 7) w.btot[(long long)blockIdx.x * 8 + threadIdx.x] = run;
+}
+
+// ---- X1': the chunk sums are already there (K3a accumulated them while it had the rows in
+// registers): only the running prefix inside each CTA's run and the CTA totals remain
+__global__ void __launch_bounds__(32) k_xs_prefix(long long nchunks, XsWork w) {
+  long long c_lo, c_hi;
+  xs_block_range(nchunks, &c_lo, &c_hi);
+  if (threadIdx.x < 7) {
+    double run = 0.0;
+    for (long long ch = c_lo; ch < c_hi; ++ch) {
+      const double v = w.csum[ch * 8 + threadIdx.x];
+      w.cpre[ch * 8 + threadIdx.x] = run;
+      run += v;
+    }
+    w.btot[(long long)blockIdx.x * 8 + threadIdx.x] = run;
+  }
 }
 
 // ---- X2: exclusive scan of the CTA totals (one CTA, tiles of 1024 with a running carry)
