@@ -2548,7 +2548,7 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
   // runs beside it on the side stream (r02 N = 8 before this: the persistent K4 CTAs held every
   // slot, K3e's later kernels queued behind them and the two ran back to back: 0.37 + 0.30 ms).
   u64 need = ((a->shard_hi - a->shard_lo) * 4 + RD_THREADS - 1) / RD_THREADS;
-  const u64 cap = (u64)c->n_sms * (a->n_ranks > 1 ? 4ull : 8ull);
+  const u64 cap = (u64)c->n_sms * (a->n_ranks >= 4 ? 4ull : a->n_ranks > 1 ? 6ull : 8ull);
   const int grid = (int)(need < cap ? (need ? need : 1) : cap);
   if (!c->ev2) { CK(cudaEventCreate(&c->ev2)); CK(cudaEventCreate(&c->ev3)); }
   CK(cudaEventRecord(c->ev2, s));
