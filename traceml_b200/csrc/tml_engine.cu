@@ -2079,7 +2079,8 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
   bool exact_win = c->world > 1 || (n - c->win_tstart) <= TML_EXACT_SUM_MAX;
   const XsSrc wsrc = xs_window_src(c, (long long)c->win_tstart, (long long)n - 1);
   const long long w_pos = (long long)(n - c->win_tstart) + wsrc.pad;
-  const bool k3a_csum = exact_win && w_pos > 1024;
+  static const bool env_csum = [] { const char* e = getenv("TML_XS_K3A_CSUM"); return !e || e[0] != '0'; }();
+  const bool k3a_csum = exact_win && w_pos > 1024 && env_csum;
   double* d_csum = nullptr;
   if (k3a_csum) {
     if (c->xs_pending) { CK(cudaStreamWaitEvent(s, c->xs_done, 0)); c->xs_pending = false; }
@@ -2548,7 +2549,9 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
   // runs beside it on the side stream (r02 N = 8 before this: the persistent K4 CTAs held every
   // slot, K3e's later kernels queued behind them and the two ran back to back: 0.37 + 0.30 ms).
   u64 need = ((a->shard_hi - a->shard_lo) * 4 + RD_THREADS - 1) / RD_THREADS;
-  const u64 cap = (u64)c->n_sms * (a->n_ranks >= 4 ? 4ull : a->n_ranks > 1 ? 6ull : 8ull);
+  static const int env_ctas = [] { const char* e = getenv("TML_K4_CTAS"); return e ? atoi(e) : 0; }();
+  const u64 per_sm = env_ctas > 0 ? (u64)env_ctas : (a->n_ranks >= 4 ? 4ull : a->n_ranks > 1 ? 6ull : 8ull);
+  const u64 cap = (u64)c->n_sms * per_sm;
   const int grid = (int)(need < cap ? (need ? need : 1) : cap);
   if (!c->ev2) { CK(cudaEventCreate(&c->ev2)); CK(cudaEventCreate(&c->ev3)); }
   CK(cudaEventRecord(c->ev2, s));
