@@ -31,11 +31,12 @@
 #include <charconv>
 
 #include "../../include/traceml_b200.h"
+#include "tml_internal.h"
 
 namespace {
 
 // ------------------------------------------------------------------ JSON helpers
-typedef std::string S;
+typedef tml_json::Str S;  // arena-backed: see tml_internal.h
 
 S fmt(const char* f, ...) {
   char buf[512];
@@ -63,27 +64,32 @@ S jstr(const S& s) {
 S jnum(double v) {
   if (!isfinite(v)) return "null";
   char buf[40];  // shortest text that round-trips the double exactly (what Python's repr prints)
-  auto r = std::to_chars(buf, buf + sizeof(buf), v);
-  S s(buf, r.ptr);
-  if (s.find_first_of(".eEn") == S::npos) s += ".0";  // keep it a JSON float
-  return s;
+  char* end = std::to_chars(buf, buf + 36, v).ptr;
+  bool is_float = false;
+  for (const char* p = buf; p < end; ++p) if (*p == '.' || *p == 'e' || *p == 'E' || *p == 'n') { is_float = true; break; }
+  if (!is_float) { *end++ = '.'; *end++ = '0'; }  // keep it a JSON float
+  return S(buf, end);
 }
-S jint(long long v) { return fmt("%lld", v); }
+S jint(long long v) {
+  char buf[24];
+  return S(buf, std::to_chars(buf, buf + sizeof(buf), v).ptr);
+}
 S jbool(bool b) { return b ? "true" : "false"; }
 const S JNULL = "null";
 S jopt_int(long long v, bool has) { return has ? jint(v) : JNULL; }
 S jopt_num(double v, bool has) { return has ? jnum(v) : JNULL; }
 
 struct Obj {
-  S s = "{";
+  S s;
   bool first = true;
+  Obj() { s.reserve(240); s += '{'; }  // one allocation for the typical object
   Obj& kv(const char* k, const S& v) {  // keys are identifiers: no escaping needed
     if (!first) s += ',';
     first = false;
     s += '"'; s += k; s += "\":"; s += v;
     return *this;
   }
-  S done() const { S o; o.reserve(s.size() + 1); o = s; o += '}'; return o; }
+  S done() { s += '}'; return std::move(s); }  // the object is spent afterwards
 };
 S jarr(const std::vector<S>& v) {
   S o = "[";
@@ -238,6 +244,7 @@ S top_ranks(const std::vector<int>& ranks, const std::vector<double>& vals) {  /
 }  // namespace
 
 extern "C" int tml_diag_step_time(const tml_st_diag_in* in, char* json_out, size_t cap) {
+  tml_json::Scope json_scope;
   if (!in || in->n_ranks < 0 || in->n_ranks > (int)TML_MAX_RANKS) return TML_ERR_ARG;
   const Thresholds th;
   const int n = in->n_ranks;
@@ -616,6 +623,7 @@ S mem_diag(const S& kind, const S& sev, const S& metric, long long steps, const 
 }  // namespace
 
 extern "C" int tml_diag_step_memory(const tml_mem_diag_in* in, char* json_out, size_t cap) {
+  tml_json::Scope json_scope;
   if (!in || in->n_metrics < 0 || in->n_metrics > 2) return TML_ERR_ARG;
   const MemTh th;
   const char* names[2] = {"peak_allocated", "peak_reserved"};
@@ -805,6 +813,7 @@ struct RankAgg {
 }  // namespace
 
 extern "C" int tml_diag_process(const tml_proc_diag_in* in, char* json_out, size_t cap) {
+  tml_json::Scope json_scope;
   if (!in || in->n_ranks < 0 || in->n_ranks > (int)TML_MAX_RANKS) return TML_ERR_ARG;
   std::vector<RankAgg> rs;
   std::vector<int> order(in->n_ranks);

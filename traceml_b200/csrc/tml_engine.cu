@@ -617,18 +617,36 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
       // approximate sums of this 32-row tile for K3e's plan (any order will do: they only choose the
       // exponent a chunk is composed under, and that choice is verified): warp tree + 7 atomics.
       // The tile lies inside ONE 256-row chunk because chunks are aligned to row indices
-      double v6 = t_dl + t_tr;
+      // Transposed butterfly: 8 values per lane -> 4 -> 2 -> 1 while the lanes pair up over bits
+      // 4, 3, 2 (each lane passes on the half it does not keep), then two plain levels over bits
+      // 1, 0: 9 exchanges instead of 35.  Lane 4 j ends up with the tile total of value j.
+      double v[8] = {t_dl, t_fwd, t_bwd, t_opt, t_wall, t_tr, t_dl + t_tr, 0.0};
+      {
+        const bool hi = (lane & 16) != 0;
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        t_dl += shfl_xor_f64(t_dl, m); t_fwd += shfl_xor_f64(t_fwd, m); t_bwd += shfl_xor_f64(t_bwd, m);
-        t_opt += shfl_xor_f64(t_opt, m); t_wall += shfl_xor_f64(t_wall, m); t_tr += shfl_xor_f64(t_tr, m);
-        v6 += shfl_xor_f64(v6, m);
+        for (int i = 0; i < 4; ++i) {
+          const double keep = hi ? v[i + 4] : v[i], send = hi ? v[i] : v[i + 4];
+          v[i] = keep + shfl_xor_f64(send, 16);
+        }
       }
+      {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double keep = hi ? v[i + 2] : v[i], send = hi ? v[i] : v[i + 2];
+          v[i] = keep + shfl_xor_f64(send, 8);
+        }
+      }
+      {
+        const bool hi = (lane & 4) != 0;
+        const double keep = hi ? v[1] : v[0], send = hi ? v[0] : v[1];
+        v[0] = keep + shfl_xor_f64(send, 4);
+      }
+      v[0] += shfl_xor_f64(v[0], 2);
+      v[0] += shfl_xor_f64(v[0], 1);
       if (base <= csum_top) {
         double* dst = csum + ((csum_top - base) >> 8) * 8;
-        const double v = lane == 0 ? t_dl : lane == 1 ? t_fwd : lane == 2 ? t_bwd : lane == 3 ? t_opt
-                       : lane == 4 ? t_wall : lane == 5 ? t_tr : v6;
-        if (lane < 7 && v != 0.0) atomicAdd(dst + lane, v);
+        if ((lane & 3) == 0 && lane < 28 && v[0] != 0.0) atomicAdd(dst + (lane >> 2), v[0]);
       }
     }
     __syncwarp();

@@ -68,28 +68,52 @@ __device__ __forceinline__ const tml_window_row* xs_rows(const XsSrc& s) {
   return (*s.noncontig) ? s.xrows : (s.rows + s.sel_rows[0]);
 }
 
-// the seven addends of summation position p (p = 0 is the newest row); zeros past the end
-__device__ __forceinline__ void xs_addends(const tml_window_row* __restrict__ rows, const XsSrc& s, long long p,
-                                           long long n, double (&o)[7]) {
-#pragma unroll
-  for (int k = 0; k < 7; ++k) o[k] = 0.0;
+// One row of summation position p (p = 0 is the newest row), in two steps so that a caller can
+// put the loads of several rows in flight before it touches any of them: xs_row_load issues the
+// flag and row loads (no branch depends on what they return), xs_row_addends turns them into the
+// seven addends -- zeros past the end or for a row the section does not use.
+struct XsRowRaw { uint4 a, b, c; unsigned fl; bool in; };
+
+__device__ __forceinline__ XsRowRaw xs_row_load(const tml_window_row* __restrict__ rows, const XsSrc& s, long long p,
+                                                long long n) {
+  XsRowRaw r;
+  r.a = r.b = r.c = make_uint4(0u, 0u, 0u, 0u);
+  r.fl = 0u;
   p -= s.pad;
-  if (p < 0 || p >= n - s.pad) return;
-  const long long i = s.last - p;
-  if (s.flags && ((s.flags[i] & s.need) != s.need)) return;
-  const uint4* src = reinterpret_cast<const uint4*>(rows + i);
-  const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-  const double dl = __longlong_as_double((long long)((u64)a.x | ((u64)a.y << 32)));
-  const double fwd = __longlong_as_double((long long)((u64)b.x | ((u64)b.y << 32)));
-  const double bwd = __longlong_as_double((long long)((u64)b.z | ((u64)b.w << 32)));
-  const double opt = __longlong_as_double((long long)((u64)c.x | ((u64)c.y << 32)));
-  const double wall = __longlong_as_double((long long)((u64)c.z | ((u64)c.w << 32)));
+  r.in = (p >= 0 && p < n - s.pad);
+  if (r.in) {
+    const long long i = s.last - p;
+    if (s.flags) r.fl = s.flags[i];
+    const uint4* src = reinterpret_cast<const uint4*>(rows + i);
+    r.a = __ldg(src); r.b = __ldg(src + 1); r.c = __ldg(src + 2);
+  }
+  return r;
+}
+
+__device__ __forceinline__ void xs_row_addends(const XsRowRaw& r, const XsSrc& s, double (&o)[7]) {
+  const bool keep = r.in && (!s.flags || ((r.fl & s.need) == s.need));
+  const double dl = __longlong_as_double((long long)((u64)r.a.x | ((u64)r.a.y << 32)));
+  const double fwd = __longlong_as_double((long long)((u64)r.b.x | ((u64)r.b.y << 32)));
+  const double bwd = __longlong_as_double((long long)((u64)r.b.z | ((u64)r.b.w << 32)));
+  const double opt = __longlong_as_double((long long)((u64)r.c.x | ((u64)r.c.y << 32)));
+  const double wall = __longlong_as_double((long long)((u64)r.c.z | ((u64)r.c.w << 32)));
   const double compute = (fwd + bwd) + opt;
   const double traced = fmax(wall, compute);
   o[0] = dl; o[1] = fwd; o[2] = bwd; o[3] = opt;
   o[4] = s.aligned ? fmax(0.0, traced) : wall;
   o[5] = traced;
   o[6] = dl + traced;
+  if (!keep) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) o[k] = 0.0;
+  }
+}
+
+// the seven addends of summation position p; zeros past the end
+__device__ __forceinline__ void xs_addends(const tml_window_row* __restrict__ rows, const XsSrc& s, long long p,
+                                           long long n, double (&o)[7]) {
+  const XsRowRaw r = xs_row_load(rows, s, p, n);
+  xs_row_addends(r, s, o);
 }
 
 __device__ __forceinline__ double xs_pick(const double (&o)[7], int k) {
@@ -278,15 +302,22 @@ __global__ void __launch_bounds__(XS_CW * 32) k_xs_compose(const XsSrc s, long l
     lo = w.bpre[owner * 8 + k] + w.cpre[ch * 8 + k];
     e = xs_plan(lo, lo + w.csum[ch * 8 + k]);
   }
-  // ---- phase A
+  // ---- phase A: four rows per lane in flight (flags + 3 x 16 B each) before the first is used
 #pragma unroll
-  for (int it = 0; it < XS_CHUNK / 32; ++it) {
-    const int r = it * 32 + lane;
-    double o[7];
-    xs_addends(rows, s, ch * XS_CHUNK + r, n, o);
-    double* dst = sm + (r >> 6) * XS_SG + (r & 63);
+  for (int half = 0; half < 2; ++half) {
+    XsRowRaw raw[4];
 #pragma unroll
-    for (int m = 0; m < 7; ++m) dst[m * XS_SK] = o[m];
+    for (int q = 0; q < 4; ++q)
+      raw[q] = xs_row_load(rows, s, ch * XS_CHUNK + (half * 4 + q) * 32 + lane, n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = (half * 4 + q) * 32 + lane;
+      double o[7];
+      xs_row_addends(raw[q], s, o);
+      double* dst = sm + (r >> 6) * XS_SG + (r & 63);
+#pragma unroll
+      for (int m = 0; m < 7; ++m) dst[m * XS_SK] = o[m];
+    }
   }
   __syncwarp();
   // ---- phase B
@@ -393,35 +424,68 @@ __device__ __forceinline__ void xs_seq32(XsState* st, double x, u64* slow_rows) 
   *slow_rows += 32;
 }
 
-// apply entries [j, end) for as long as they apply; returns the first index that did not
+// inclusive ordered scan over the warp: lane i receives m[0] o m[1] o ... o m[i] (m[0] applied
+// first).  Raw maps: 32 sealed maps (< 2^53 each) stay below 2^58.
+__device__ __forceinline__ XsFn xs_warp_scan_raw(XsFn m, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    XsFn p;
+    p.c0 = __shfl_up_sync(0xffffffffu, m.c0, d);
+    p.c1 = __shfl_up_sync(0xffffffffu, m.c1, d);
+    if (lane >= d) m = xs_compose_raw(p, m);
+  }
+  return m;
+}
+
+// Apply entries [j, end) for as long as they apply; returns the first index that did not.  The
+// whole warp works on 32 entries at a time: lane i composes entries j .. j+i (the maps are
+// associative), applies that prefix to the running sum and the warp keeps the longest prefix that
+// stays inside the binade -- the increments are non-negative, so "entry i overflows" is monotone in
+// i and the result equals applying the entries one after the other.  `e` == nullptr: every entry
+// was composed under exponent `e_all`.
 __device__ __forceinline__ int xs_apply_run(XsState* st, const XsFn* __restrict__ f, const int* __restrict__ e,
-                                            int j, int end) {
+                                            int e_all, int j, int end, int lane) {
   const int eb = st->eb;
   u64 S = st->S;
-#pragma unroll 4
-  for (; j < end; ++j) {
-    const int E = e[j];
-    if (E == XS_PLAN_ZERO) continue;
-    if (E != eb || E < 1) break;
-    const XsFn m = f[j];
-    const u64 S2 = S + ((S & 1ull) ? m.c1 : m.c0);
-    if (m.c0 == ~0ull || (S2 >> 53)) break;
-    S = S2;
+  while (j < end) {
+    const int idx = j + lane;
+    int E = XS_PLAN_ZERO;
+    XsFn m = xs_identity();
+    if (idx < end) { E = e ? e[idx] : e_all; m = f[idx]; }
+    const bool zero = (E == XS_PLAN_ZERO);
+    const bool ok = zero || (E == eb && E >= 1 && E < 0x7ff && m.c0 != ~0ull);
+    const unsigned bad = __ballot_sync(0xffffffffu, !ok);
+    const int nvalid = bad ? (__ffs(bad) - 1) : 32;
+    if (zero || lane >= nvalid) m = xs_identity();
+    const XsFn pre = xs_warp_scan_raw(m, lane);
+    const u64 Si = S + ((S & 1ull) ? pre.c1 : pre.c0);
+    const unsigned ov = __ballot_sync(0xffffffffu, (Si >> 53) != 0ull);
+    int napply = ov ? (__ffs(ov) - 1) : 32;
+    napply = napply < nvalid ? napply : nvalid;
+    if (napply > 0) S = __shfl_sync(0xffffffffu, Si, napply - 1);
+    j += napply;
+    if (napply < 32) break;
   }
   st->S = S;
-  return j;
+  return j < end ? j : end;
 }
 
 // one crossing chunk: tile maps `tm` (exponents ea, ea + 1) staged in shared memory, the chain's
 // addends in the slot (global): only the tile that crosses is fetched and added row by row
 __device__ __forceinline__ void xs_walk_tiles(const double* __restrict__ xraw, long long p0, long long n, int lane,
                                               const XsTileHead* tm, int ea, XsState* st, u64* slow_rows) {
+  const long long left = (n - p0 + 31) / 32;
+  const int nt = left < XS_TILES ? (int)left : XS_TILES;
+  int t = 0;
 #pragma unroll 1
-  for (int t = 0; t < XS_TILES; ++t) {
-    if (p0 + t * 32 >= n) break;
+  while (t < nt) {
     const int h = st->eb - ea;
-    if ((h == 0 || h == 1) && xs_apply_s(st->eb, &st->S, tm->f[h][t], st->eb)) continue;
+    if (h == 0 || h == 1) {
+      t = xs_apply_run(st, tm->f[h], nullptr, st->eb, t, nt, lane);
+      if (t >= nt) break;
+    }
     xs_seq32(st, xraw[t * 32 + lane], slow_rows);
+    ++t;
   }
 }
 
@@ -531,7 +595,7 @@ __global__ void __launch_bounds__(256, 1) k_xs_walk(const XsSrc s, long long n, 
     if (warp == 0) {
       int next_inv = 0;
       for (int j = 0; j < cnt; ++j) {
-        j = xs_apply_run(&st, s_g, s_ge, j, cnt);
+        j = xs_apply_run(&st, s_g, s_ge, 0, j, cnt, lane);
         if (j >= cnt) break;
         const long long c0 = (gb + j) * XS_GROUP;
         int gi = XS_IG;  // spare row
@@ -547,7 +611,7 @@ __global__ void __launch_bounds__(256, 1) k_xs_walk(const XsSrc s, long long n, 
           __syncwarp();
         }
         for (int q = 0; q < XS_GROUP; ++q) {
-          q = xs_apply_run(&st, s_c[gi], s_ce[gi], q, XS_GROUP);
+          q = xs_apply_run(&st, s_c[gi], s_ce[gi], 0, q, XS_GROUP, lane);
           if (q >= XS_GROUP) break;
           const int CE = s_ce[gi][q];
           const long long p0 = (c0 + q) * XS_CHUNK;

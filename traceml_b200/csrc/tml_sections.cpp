@@ -26,30 +26,37 @@
 
 namespace {
 
-typedef std::string S;
+typedef tml_json::Str S;  // arena-backed: see tml_internal.h
 
 S jnum(double v) {
   if (!std::isfinite(v)) return "null";
   char buf[40];
-  auto r = std::to_chars(buf, buf + sizeof(buf), v);
-  S s(buf, r.ptr);
-  if (s.find_first_of(".eEn") == S::npos) s += ".0";
-  return s;
+  char* end = std::to_chars(buf, buf + 36, v).ptr;
+  bool is_float = false;
+  for (const char* p = buf; p < end; ++p) if (*p == '.' || *p == 'e' || *p == 'E' || *p == 'n') { is_float = true; break; }
+  if (!is_float) { *end++ = '.'; *end++ = '0'; }
+  return S(buf, end);
 }
-S jint(long long v) { return std::to_string(v); }
+S jint(long long v) {
+  char buf[24];
+  return S(buf, std::to_chars(buf, buf + sizeof(buf), v).ptr);
+}
 S jq(const S& s) { return "\"" + s + "\""; }  // keys / labels here never need escaping
 const S JNULL = "null";
 
 struct Obj {
-  S s = "{";
+  S s;
   bool first = true;
-  Obj& kv(const S& k, const S& v) {
+  explicit Obj(size_t hint = 240) { s.reserve(hint); s += '{'; }
+  Obj& kv(const char* k, size_t kn, const S& v) {
     if (!first) s += ',';
     first = false;
-    s += '"'; s += k; s += "\":"; s += v;
+    s += '"'; s.append(k, kn); s += "\":"; s += v;
     return *this;
   }
-  S done() const { S o; o.reserve(s.size() + 1); o = s; o += '}'; return o; }
+  Obj& kv(const char* k, const S& v) { return kv(k, strlen(k), v); }
+  Obj& kv(const S& k, const S& v) { return kv(k.data(), k.size(), v); }
+  S done() { s += '}'; return std::move(s); }  // the object is spent afterwards
 };
 
 struct RankSummary {  // RankStepSummary
@@ -166,6 +173,7 @@ enum { S_DL, S_FWD, S_BWD, S_OPT, S_STEP, S_WAIT, S_ALLOC, S_RESV };
 
 extern "C" int tml_sections_json(const tml_reduce_run_out* o, const tml_sections_args* a, char* json_out,
                                  size_t cap) {
+  tml_json::Scope json_scope;
   if (!o || !a || !json_out) return TML_ERR_ARG;
   const int R = (int)o->n_ranks;
   if (R < 1 || R > (int)TML_MAX_RANKS) return TML_ERR_ARG;
