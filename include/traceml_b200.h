@@ -325,7 +325,9 @@ typedef struct tml_reduce_args {
  * reporting/sections/step_memory/model.py:141-176. */
 int tml_win_reduce(tml_ctx* ctx, const tml_reduce_args* args, void* stream);
 /* Device time (ms, CUDA events on the launching stream) of the last k_window_rows
- * (which = 0) / k_window_reduce (which = 1) launch; -1 if none or not finished. */
+ * (which = 0) / k_window_reduce (which = 1) launch; -1 if none or not finished.
+ * Timeline of the last reduce, ms since k_window_rows began: which = 2 the reduce kernel's
+ * launch point, 3 the end of the deferred exact sums (side stream), 4 the reduce kernel's end. */
 double tml_kernel_ms(tml_ctx* ctx, uint32_t which);
 
 typedef struct tml_band_args {

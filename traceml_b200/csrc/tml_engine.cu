@@ -1126,6 +1126,7 @@ __global__ void __launch_bounds__(GA_THREADS) k_gather(const tml_window_row* __r
 // the deterministic tree sums of K3a (rel <= 1e-13) and skips the two extra passes over its rows.
 
 #define TML_EXACT_SUM_MAX (1u << 17)
+#define XS_COMPOSE_CTAS_BESIDE_K4 0  // 0: no cap (smem allows 7 per SM)
 
 #include "tml_exact_sum.cuh"
 
@@ -1158,6 +1159,7 @@ struct ReduceParams {
   u64 n_common, shard_lo, shard_hi;
   u32 mask;
   u32 n_ranks;
+  unsigned long long* ticket;  // next tile to hand out (zeroed before the launch); NULL: static grid-stride
 };
 
 #define RD_THREADS 256
@@ -1168,7 +1170,7 @@ struct ReduceParams {
 // kernel writes twice what it reads at small R, so store locality decides its HBM
 // efficiency.
 template <int R, int U>
-__global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_constant__ ReduceParams p) {
+__global__ void __launch_bounds__(RD_THREADS, (R <= 2 ? 8 : R <= 4 ? 5 : 3)) k_window_reduce(const __grid_constant__ ReduceParams p) {
   __shared__ double s_out[TML_SERIES_PER_STEP][RD_THREADS / 4];
   const int q = threadIdx.x & 3, row = threadIdx.x >> 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1177,8 +1179,24 @@ __global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_const
   const u64 n = p.n_common;
   double* __restrict__ S = p.series;
   const bool do_time = (p.mask & TML_MASK_TIME) != 0u, do_mem = (p.mask & TML_MASK_MEM) != 0u;
+  // Tiles are handed out by a ticket counter, not by a fixed stride: beside K3e only part of the
+  // grid is resident at first (the compose CTAs hold most of every SM for ~0.1 ms), and with a
+  // fixed stride the CTAs that get in late would still have their whole share to do -- the kernel
+  // would last until the last of them is done.  With tickets whoever is resident pulls work, late
+  // CTAs find none.  Thread 0 draws the next ticket at the top of a trip (its latency hides under
+  // the row loads) and publishes it between the trip's two barriers.
+  __shared__ u64 s_tb;
+  unsigned long long* const ticket = p.ticket;
+  u64 tb = (u64)blockIdx.x * RD_THREADS;
+  if (ticket) {
+    if (threadIdx.x == 0) s_tb = (u64)atomicAdd(ticket, 1ull) * RD_THREADS;
+    __syncthreads();
+    tb = s_tb;
+  }
   // block-uniform trip count: the width-4 shuffles and the barriers need every thread
-  for (u64 tb = (u64)blockIdx.x * RD_THREADS; tb < work; tb += nthreads) {
+  while (tb < work) {
+    u64 next_tb = tb + nthreads;
+    if (ticket && threadIdx.x == 0) next_tb = (u64)atomicAdd(ticket, 1ull) * RD_THREADS;
     const u64 t = tb + threadIdx.x;
     const bool ok = t < work;
     const u64 j = p.shard_lo + (t >> 2);
@@ -1231,7 +1249,9 @@ __global__ void __launch_bounds__(RD_THREADS) k_window_reduce(const __grid_const
         }
       }
     }
+    if (ticket && threadIdx.x == 0) s_tb = next_tb;
     __syncthreads();
+    tb = ticket ? s_tb : next_tb;
   }
 }
 
@@ -1469,6 +1489,7 @@ struct tml_ctx {
   // host-side step state (training thread)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of k_window_rows alone
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // device time of k_window_reduce alone
+  unsigned long long* d_ticket = nullptr;    // K4's tile counter
   cudaEvent_t ev_proc = nullptr;             // the process aggregates have reached the staging slot
   u64 commits = 0;
   u64 launches = 0;  // kernels this context has launched (bench: gpu_launches)
@@ -1600,7 +1621,22 @@ static int launch_exact_sums(tml_ctx* c, const XsSrc& src, double* d_out, cudaSt
     {
       long long per = (nchunks + grid - 1) / grid;  // X1's run length (xs_block_range)
       per = (per + XS_WARPS - 1) / XS_WARPS * XS_WARPS;
-      k_xs_compose<<<(int)((nchunks + XS_CW - 1) / XS_CW), XS_CW * 32, 0, s>>>(src, n, nchunks, w, (int)per);
+      // beside K4 (deferred launch on the side stream) the compose CTAs must leave room for K4's:
+      // dynamic shared memory that nobody touches caps them per SM (228 KB / (30 KB static + pad))
+      static const int env_ctas = [] { const char* e = getenv("TML_XS_COMPOSE_CTAS"); return e ? atoi(e) : 0; }();
+      int pad_bytes = 0;
+      const int per_sm = env_ctas > 0 ? env_ctas : (s == c->xs_stream ? XS_COMPOSE_CTAS_BESIDE_K4 : 0);
+      if (per_sm >= 1 && per_sm < 7) {
+        pad_bytes = (int)(228 * 1024 / per_sm) - 32 * 1024;  // static 30 016 B + 1 KB reserved per CTA
+        if (pad_bytes > 0) {
+          static int attr_set = 0;
+          if (attr_set < pad_bytes) {
+            CK(cudaFuncSetAttribute(k_xs_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_bytes));
+            attr_set = pad_bytes;
+          }
+        } else pad_bytes = 0;
+      }
+      k_xs_compose<<<(int)((nchunks + XS_CW - 1) / XS_CW), XS_CW * 32, pad_bytes, s>>>(src, n, nchunks, w, (int)per);
     }
     CK(cudaPeekAtLastError());
     k_xs_groups<<<(int)((ngroups * 7 + 7) / 8), 256, 0, s>>>(w, nchunks, ngroups);
@@ -1700,6 +1736,7 @@ int tml_shutdown(tml_ctx* c) {
   if (c->xs_stream) cudaStreamDestroy(c->xs_stream);
   if (c->xs_gate) cudaEventDestroy(c->xs_gate);
   if (c->xs_done) cudaEventDestroy(c->xs_done);
+  if (c->d_ticket) cudaFree(c->d_ticket);
   cudaFree(c->d_partials); cudaFree(c->d_final); cudaFree(c->d_bandcnt);
   cudaFree(c->d_ppartials); cudaFree(c->d_pfinal);
   cudaFreeHost(c->h_stage);
@@ -2125,7 +2162,7 @@ int tml_win_prepare(tml_ctx* c, uint32_t window, void* stream, tml_win_info* out
       CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       CK(cudaStreamCreateWithPriority(&c->xs_stream, cudaStreamNonBlocking, prio_hi));
       CK(cudaEventCreateWithFlags(&c->xs_gate, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&c->xs_done, cudaEventDisableTiming));
+      CK(cudaEventCreate(&c->xs_done));  // timed: tml_kernel_ms(3)
     }
     CK(cudaEventRecord(c->xs_gate, s));
     CK(cudaStreamWaitEvent(c->xs_stream, c->xs_gate, 0));
@@ -2561,17 +2598,25 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
   p.series = a->series; p.n_common = a->n_common;
   p.shard_lo = a->shard_lo; p.shard_hi = a->shard_hi;
   p.mask = a->mask; p.n_ranks = a->n_ranks;
-  // 32 regs x 256 threads: 8 CTAs/SM could be resident; a multiple of the SM count, grid-stride
-  // inside.  With several ranks the kernel is NVLink-bound -- 4 CTAs/SM already keep 16 x the
-  // bandwidth-delay product in flight -- and the other half of every SM is left to K3e, which
-  // runs beside it on the side stream (r02 N = 8 before this: the persistent K4 CTAs held every
-  // slot, K3e's later kernels queued behind them and the two ran back to back: 0.37 + 0.30 ms).
+  // A multiple of the SM count; the CTAs pull tiles from a ticket counter.  One rank: 8 CTAs/SM
+  // (29 regs), HBM-bound.  Several ranks: NVLink-bound -- two CTAs of 256 threads x R loads already
+  // keep several bandwidth-delay products in flight per SM -- and K3e runs beside it on the side
+  // stream, so the cap leaves the registers of one walk CTA free on every SM (r02 timeline on 8
+  // ranks before this: the persistent K4 CTAs held every SM, the walk started when K4 had finished).
   u64 need = ((a->shard_hi - a->shard_lo) * 4 + RD_THREADS - 1) / RD_THREADS;
   static const int env_ctas = [] { const char* e = getenv("TML_K4_CTAS"); return e ? atoi(e) : 0; }();
-  const u64 per_sm = env_ctas > 0 ? (u64)env_ctas : (a->n_ranks >= 4 ? 4ull : a->n_ranks > 1 ? 6ull : 8ull);
+  // registers decide what fits beside K3e's walk (16 K): R = 2: 6 x 8 K, R = 3..4: 4 x 12 K, R >= 5: 2 x 20 K
+  const u64 per_sm = env_ctas > 0 ? (u64)env_ctas
+                     : (a->n_ranks >= 5 ? 2ull : a->n_ranks >= 3 ? 4ull : a->n_ranks > 1 ? 6ull : 8ull);
   const u64 cap = (u64)c->n_sms * per_sm;
   const int grid = (int)(need < cap ? (need ? need : 1) : cap);
   if (!c->ev2) { CK(cudaEventCreate(&c->ev2)); CK(cudaEventCreate(&c->ev3)); }
+  static const bool env_ticket = [] { const char* e = getenv("TML_K4_TICKET"); return !e || e[0] != '0'; }();
+  if (env_ticket && a->n_ranks <= 8) {
+    if (!c->d_ticket) CK(cudaMalloc(&c->d_ticket, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned long long), s));
+    p.ticket = c->d_ticket;
+  }
   CK(cudaEventRecord(c->ev2, s));
   switch (a->n_ranks) {
     case 1: launch_reduce<1>(grid, s, p); break;
@@ -2591,8 +2636,9 @@ int tml_win_reduce(tml_ctx* c, const tml_reduce_args* a, void* stream) {
 }
 
 double tml_kernel_ms(tml_ctx* c, uint32_t which) {
-  if (!c || which > 1) return -1.0;
-  cudaEvent_t a = which == 0 ? c->ev0 : c->ev2, b = which == 0 ? c->ev1 : c->ev3;
+  if (!c || which > 4) return -1.0;
+  cudaEvent_t a = which == 1 ? c->ev2 : c->ev0;
+  cudaEvent_t b = which == 0 ? c->ev1 : which == 2 ? c->ev2 : which == 3 ? c->xs_done : c->ev3;
   if (!a || !b) return -1.0;
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return -1.0; }

@@ -513,7 +513,9 @@ __device__ __forceinline__ void xs_walk_rows(const tml_window_row* rows, const X
   }
 }
 
-__global__ void __launch_bounds__(256, 1) k_xs_walk(const XsSrc s, long long n, long long nchunks, long long ngroups,
+// <= 64 registers: a walk CTA (16 K registers) must fit on an SM beside the resident K4 CTAs -- at
+// 128 it did not, and on 8 ranks the walk started only when K4 had finished (r02 timeline)
+__global__ void __launch_bounds__(256, 4) k_xs_walk(const XsSrc s, long long n, long long nchunks, long long ngroups,
                                                  XsWork w, int planned, double* __restrict__ out,
                                                  unsigned long long* __restrict__ stats /* [7]: rows added one by one */) {
   __shared__ XsFn s_g[XS_GB];

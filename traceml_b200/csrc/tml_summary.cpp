@@ -788,6 +788,14 @@ extern "C" int tml_reduce_run(tml_ctx* c, const tml_comm* comm, const tml_reduce
   out->n_exchanges = r.n_exchanges;
   out->k3a_ms = info.kernel_ms;
   out->k4_ms = tml_kernel_ms(c, 1);
+  {
+    // TML_TIMELINE=1: device timeline of this reduce on stderr (rank 0), ms since K3a began
+    static const bool tl = [] { const char* e = getenv("TML_TIMELINE"); return e && e[0] == '1'; }();
+    if (tl && r.rank == 0)
+      fprintf(stderr, "[tml timeline] k3a_end %.3f k4_launch %.3f k3e_end %.3f k4_end %.3f | host prepare %.3f "
+              "align %.3f reduce %.3f bands %.3f\n", info.kernel_ms, tml_kernel_ms(c, 2), tml_kernel_ms(c, 3),
+              tml_kernel_ms(c, 4), t1 - t0, t2 - t1, t3 - t2, t4 - t3);
+  }
   out->stage_ms[0] = t1 - t0; out->stage_ms[1] = t2 - t1; out->stage_ms[2] = t3 - t2;
   out->stage_ms[3] = t4 - t3; out->stage_ms[4] = t4 - t0;
   return TML_OK;
