@@ -430,7 +430,11 @@ def run_reference(args, rank, world):
     R = max(1, args.gpus)
     W = int(args.window)
     K, Wm = max(1, args.steps), max(0, args.warmup)
-    Ws = max(500, args.sample // R)  # bounded: ~40 000 rows in all, a few seconds per step
+    # Bounded sample per step, sized by K so that the whole run ends within minutes whatever
+    # --steps says: the reference costs ~100 us per row (single-threaded Python), so K + W steps of
+    # `rows` rows take (K + W) * rows * 1e-4 s; aim at ~100 s in all, never above --sample rows.
+    budget_rows = int(100.0 / 1.0e-4 / (K + Wm))
+    Ws = max(500, min(args.sample, budget_rows) // R)
     line = {
         "impl": "reference", "metric": "cross_rank_reduce_GBps", "unit": "GB/s", "n_gpus": args.gpus,
         "steps": K, "warmup": Wm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
