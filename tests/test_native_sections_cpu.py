@@ -114,3 +114,50 @@ def test_tie_breaks_with_identical_ranks(pattern):
     for k in ("average", "median", "worst"):
         assert_struct(plain(nat["step_time"]["global"][k]), plain(o["global"][k]), f"oracle.global.{k}", rel=0.0)
     assert_struct(plain(nat["step_time"]["diagnosis"]), plain(o["diagnosis"]), "oracle.diagnosis", rel=0.0)
+
+
+def test_sections_json_from_several_threads():
+    """The JSON strings of one call come from a per-thread bump arena (tml_internal.h) that is
+    rewound when the outermost entry point returns: calls racing on different threads (ctypes
+    drops the GIL) must not see each other's memory."""
+    import ctypes as C
+    import threading
+
+    from fake_engine import FakeEngine
+    import replay
+    from traceml_b200 import _abi, sections
+
+    outs = {}
+    for R in (1, 3, 8):
+        W = 300
+        recs = replay.make_step_replay("input_straggler", R, W, seed=R)
+        procs = replay.make_proc_replay("normal", R, W, seed=R)
+        se = sections.SummaryEngine([FakeEngine(recs[r], procs[r]) for r in range(R)],
+                                    ram_total=replay.PROC_RAM_TOTAL_BYTES, gpu_count=R)
+        se.reducer.device = torch.device("cpu")
+        red = se.build(W, W).pop("reduce")
+        outs[R] = (fill_run_out(red, W, W), R, W)
+    lib = _abi.lib()
+    want = {}
+    for R, (o, _, W) in outs.items():
+        buf = C.create_string_buffer(1 << 18)
+        args = _abi.SectionsArgs(float(replay.PROC_RAM_TOTAL_BYTES), R, W, W, 0)
+        assert lib.tml_sections_json(C.byref(o), C.byref(args), buf, len(buf)) == 0
+        want[R] = buf.value
+    bad = []
+
+    def worker(R):
+        o, _, W = outs[R]
+        buf = C.create_string_buffer(1 << 18)
+        args = _abi.SectionsArgs(float(replay.PROC_RAM_TOTAL_BYTES), R, W, W, 0)
+        for _ in range(300):
+            if lib.tml_sections_json(C.byref(o), C.byref(args), buf, len(buf)) != 0 or buf.value != want[R]:
+                bad.append(R)
+                return
+
+    threads = [threading.Thread(target=worker, args=(R,)) for R in (1, 3, 8, 1, 3, 8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not bad, bad
