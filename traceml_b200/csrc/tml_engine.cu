@@ -615,8 +615,8 @@ __global__ void __launch_bounds__(WR_THREADS, 2) k_window_rows(
     }
     if (csum) {
       // approximate sums of this 32-row tile for K3e's plan (any order will do: they only choose the
-      // exponent a chunk is composed under, and that choice is verified): warp tree + 7 atomics.
-      // The tile lies inside ONE 256-row chunk because chunks are aligned to row indices
+      // exponent a chunk is composed under, and that choice is verified when the map is applied).
+      // The tile lies inside ONE 256-row chunk because chunks are aligned to row indices.
       // Transposed butterfly: 8 values per lane -> 4 -> 2 -> 1 while the lanes pair up over bits
       // 4, 3, 2 (each lane passes on the half it does not keep), then two plain levels over bits
       // 1, 0: 9 exchanges instead of 35.  Lane 4 j ends up with the tile total of value j.

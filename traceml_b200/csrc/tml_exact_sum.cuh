@@ -2,21 +2,23 @@
 // bit for bit, for any window size (math and rationale: tml_exact_sum.h).  Included by
 // tml_engine.cu; replaces round 1's single-thread dependency chain (k_seq_sums, <= 2^17 rows).
 //
-// Work unit: a CHUNK of 256 consecutive rows (in summation order) = one warp, lane l owning the 8
-// consecutive rows 8l .. 8l+7, so the ordered composition is 8 serial steps per lane plus ONE
-// 5-level shuffle tree per chunk and chain.  A CTA owns a contiguous run of chunks.
+// Work unit: a CHUNK of 256 consecutive rows (in summation order) = one warp of the compose kernel;
+// 32 chunks = one GROUP.  Maps compose associatively, so every level is built in parallel and only
+// the walk -- a few hundred map applications plus one 32-row tile per binade crossing -- is serial.
 //
-//   X1 k_xs_partial   chunk -> 7 approximate sums + their running prefix inside the CTA's run
+//   X1 k_xs_prefix    running prefix of the approximate chunk sums K3a left in the workspace
+//      (k_xs_partial  computes those sums in a pass of its own: aligned sources, TML_XS_K3A_CSUM=0)
 //   X2 k_xs_bscan     exclusive scan of the CTA totals (one small CTA)
 //   X3 k_xs_compose   chunk -> exponent plan + 7 (c0, c1) maps; for a chunk whose running sum
 //                     changes binade: the eight 32-row TILE maps under both candidate exponents
 //   X3b k_xs_groups   32 chunks -> one map (warp-ordered composition)
-//   X4 k_xs_walk      one warp per chain: groups -> chunks -> tiles; only the tile that contains
-//                     a binade crossing (and the start-up from 0) is redone with real adds
+//   X4 k_xs_walk      one CTA per chain: groups -> chunks -> tiles, 32 maps per warp step; only the
+//                     tile that contains a binade crossing (and the start-up from 0) is redone with
+//                     real adds
 //
-// Rows are read twice (X1, X3): 128 B/row of local HBM traffic.  At R > 1 that hides under the
-// NVLink-bound K4 on a side stream; the R = 1 bulk path does not need reference-order sums at all
-// (no second rank to break a tie against) and skips K3e.
+// Window sums read the rows once (X3: 64 B/row; the chunk sums come out of K3a's registers), aligned
+// sums twice.  At R > 1 K3e runs beside the NVLink-bound K4 on a side stream; the R = 1 bulk path
+// does not need reference-order sums at all (no second rank to break a tie against) and skips K3e.
 #pragma once
 #include "tml_exact_sum.h"
 
@@ -271,14 +273,15 @@ __global__ void __launch_bounds__(1024) k_xs_bscan(XsWork w, int nblocks) {
   if (t == 0) *w.nslots = 0u;
 }
 
-// ---- X3.  One warp per chunk.  Phase A: lane = row (8 passes of 32 rows, every load of a pass in
-// flight at once); the seven addends of a row are derived ONCE and parked in shared memory, chain
-// by chain.  Phase B: lane = (g, k), row quarter g = lane >> 3 (64 consecutive rows), chain
-// k = lane & 7 (k == 7 idles): a lane walks its 64 rows serially for ITS chain -- one LDS, one
-// branch-free FPU element map, one branch-free compose per row -- and the four quarters of a chain
-// are joined by two shuffle levels.  ncu history (W = 4e6, 28 M element maps): v1 lane = 8 rows x 7
-// chains from global memory, 95 M warp instructions, 217 us; v3 lane = (g, k) deriving all seven
-// addends per lane, 209 M, 197 us; this version: see profiles/.
+// ---- X3.  One warp per chunk.  Phase A: lane = row (two passes of four rows per lane, the flag and
+// row loads of a pass all in flight before the first is used); the seven addends of a row are
+// derived ONCE and parked in shared memory, chain by chain.  Phase B: lane = (g, k), row quarter
+// g = lane >> 3 (64 consecutive rows), chain k = lane & 7 (k == 7 idles): a lane walks its 64 rows
+// serially for ITS chain -- one LDS, one branch-free FPU element map, one branch-free compose per
+// row -- and the four quarters of a chain are joined by two shuffle levels.  ncu history (W = 4e6,
+// 28 M element maps): v1 lane = 8 rows x 7 chains from global memory, 95 M warp instructions, 217 us;
+// v3 lane = (g, k) deriving all seven addends per lane, 209 M, 197 us; v5 shared-memory staging,
+// flag -> row loads one after the other, 100 us; this version 88 us (profiles/r02_summary.md).
 #define XS_CW 2                    // warps (chunks in flight) per compose CTA
 #define XS_SG 65                   // doubles per row quarter (64 + 1: quarters in different banks)
 #define XS_SK (4 * XS_SG + 8)      // doubles per chain
