@@ -79,3 +79,32 @@ def test_two_rank_reduce_matches_oracle(scenario, S, W, exchange):
     procs = replay.make_proc_replay("overhang", world, 200, seed=3)
     pref = process_oracle.process_section(oracle_proc_rows(procs, world), max_rows=W)
     assert_struct(plain(got[0]["process"]["primary"]), plain(pref["diagnosis"]["primary"]), "proc.primary")
+
+
+def _host_worker(rank, world, init_file, out_dir, fake_other_host):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    import socket
+
+    from traceml_b200.reduce import TorchDistComm
+
+    if fake_other_host and rank == 1:
+        socket.gethostname = lambda: "some-other-node"
+    comm = TorchDistComm()
+    first = comm.one_host(torch.device("cpu"))
+    socket.gethostname = lambda: f"changed-after-{rank}"   # cached: no second collective, same answer
+    second = comm.one_host(torch.device("cpu"))
+    torch.save((first, second), os.path.join(out_dir, f"h{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fake_other_host", [False, True])
+def test_one_host_check_is_collective_once_and_agrees(fake_other_host):
+    """CUDA-IPC peer loads (the p2p row exchange) need every rank on one host: the check behind
+    the ``auto`` choice, over gloo."""
+    world = 2
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_host_worker, args=(world, os.path.join(td, "init"), td, fake_other_host), nprocs=world, join=True)
+        got = [torch.load(os.path.join(td, f"h{r}.pt"), weights_only=False) for r in range(world)]
+    assert got[0] == got[1] == ((not fake_other_host),) * 2

@@ -76,3 +76,35 @@ def test_summary_artifacts_are_written_atomically(tmp_path):
     write_summary_artifacts(dict(env, text="again"), str(tmp_path / "session"))  # replace in place
     assert open(paths["txt"]).read() == "again"
     assert sorted(p.name for p in (tmp_path / "session").iterdir()) == ["final_summary.json", "final_summary.txt"]
+
+
+def test_auto_exchange_avoids_p2p_across_hosts():
+    """``auto`` picks the CUDA-IPC peer-load exchange from 10^6 aligned rows per rank -- only when
+    every rank is a process of this host (reduce.py:_exchange_mode, run_native)."""
+    import torch
+    from fake_engine import FakeEngine
+    import replay
+    from traceml_b200.reduce import WindowReducer
+
+    class Comm:
+        world, index = 2, 0
+
+        def __init__(self, same):
+            self.same, self.asked = same, 0
+
+        def one_host(self, device=None):
+            self.asked += 1
+            return self.same
+
+    eng = FakeEngine(replay.make_step_replay("balanced", 1, 8, seed=0)[0], None)
+    for same, big in ((True, "p2p"), (False, "a2a")):
+        red = WindowReducer([eng], Comm(same), device=torch.device("cuda", 0), exchange="auto")
+        assert red._exchange_mode(10_000) == "a2a"            # small windows never map peers
+        assert red._exchange_mode(2_000_000) == big
+        assert red._spec_len() == (15 + 72 if same else 15)   # no IPC handle in the first exchange
+    red = WindowReducer([eng], Comm(False), device=torch.device("cuda", 0), exchange="p2p")
+    assert red._exchange_mode(2_000_000) == "p2p"             # an explicit request is honoured
+    # a communicator object without the method (user-supplied): assume one host, as before
+    class Bare:
+        world, index = 2, 0
+    assert WindowReducer([eng], Bare(), device=torch.device("cuda", 0))._exchange_mode(2_000_000) == "p2p"

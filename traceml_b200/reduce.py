@@ -69,6 +69,9 @@ class LocalComm:
     def nccl_comm_ptr(self, device) -> Optional[int]:
         return None
 
+    def one_host(self, device=None) -> bool:
+        return True
+
 
 class TorchDistComm:
     """torch.distributed plumbing (NCCL over NVLink on the box, gloo in CPU tests)."""
@@ -80,8 +83,28 @@ class TorchDistComm:
         self.group = group
         self.n_vec = 0  # small vector all-gathers issued (the latency-bound exchanges)
         self._comm_ptr: Optional[int] = None
+        self._one_host: Optional[bool] = None
         self.world = dist.get_world_size(group)
         self.index = dist.get_rank(group)
+
+    def one_host(self, device=None) -> bool:
+        """Do all ranks of the group run on this host?  CUDA-IPC peer mappings (the ``p2p`` row
+        exchange) exist only between processes of one host.  Collective on its first call (one
+        all-gather of a 48-bit host-name hash), cached afterwards."""
+        if self._one_host is None:
+            if self.world == 1:
+                self._one_host = True
+            else:
+                import hashlib
+                import socket
+
+                h = int.from_bytes(hashlib.blake2b(socket.gethostname().encode(), digest_size=6).digest(), "big")
+                dev = device or torch.device("cpu")
+                inp = torch.tensor([float(h)], dtype=torch.float64, device=dev)  # < 2^48: exact in f64
+                out = torch.empty(self.world, dtype=torch.float64, device=dev)
+                self._dist.all_gather_into_tensor(out, inp, group=self.group)
+                self._one_host = bool((out == out[0]).all().item())
+        return self._one_host
 
     def nccl_comm_ptr(self, device: torch.device) -> Optional[int]:
         """The ncclComm_t torch.distributed already holds for this group and device (the
@@ -244,6 +267,11 @@ class WindowReducer:
         self.exchange = exchange
         self._p2p_warm = False  # peer mappings already open: p2p costs nothing extra
         self._k4_events: List[Any] = []
+
+    def _peers_on_this_host(self) -> bool:
+        """CUDA-IPC (p2p) is possible: every rank of the group is a process of this host."""
+        fn = getattr(self.comm, "one_host", None)
+        return True if fn is None else bool(fn(self.device))
 
     # global rank of local engine l
     def _grank(self, l: int) -> int:
@@ -455,7 +483,10 @@ class WindowReducer:
         eng = self.engines[0]
         world = self.comm.world
         ptr = self.comm.nccl_comm_ptr(self.device) if world > 1 else 0
-        return eng.reduce_run(window, int(proc_rows or 0), self.exchange if self.exchange in _abi.XCHG else "auto",
+        xchg = self.exchange if self.exchange in _abi.XCHG else "auto"
+        if xchg == "auto" and world > 1 and not self._peers_on_this_host():
+            xchg = "a2a"  # the native driver's own "auto" assumes one host (p2p from 10^6 rows)
+        return eng.reduce_run(window, int(proc_rows or 0), xchg,
                               self.speculate, ptr or 0, self.comm.index, world,
                               _stream_of(self.device) if stream is None else stream)
 
@@ -515,7 +546,8 @@ class WindowReducer:
         """Length of the speculative alignment block in the first exchange (0 = off)."""
         if not self.speculate:
             return 0
-        handles = self.comm.world > 1 and self.device.type == "cuda" and self.exchange in ("auto", "p2p")
+        handles = self.comm.world > 1 and self.device.type == "cuda" and (
+            self.exchange == "p2p" or (self.exchange == "auto" and self._peers_on_this_host()))
         return _ALIGN_LEN if handles else 15
 
     def _align(self, kind: int, window: int, infos, ranks, stream, spec=None) -> KindResult:
@@ -619,6 +651,8 @@ class WindowReducer:
         if self.device.type != "cuda":
             return "nccl"
         if n_common is not None and n_common < self.P2P_MIN_ROWS and not self._p2p_warm:
+            return "a2a" if self.L == 1 else "nccl"
+        if not self._peers_on_this_host():  # ranks on other hosts: no peer mappings to load through
             return "a2a" if self.L == 1 else "nccl"
         return "p2p"
 
