@@ -121,7 +121,10 @@ def final_summary(*, timeout_sec: float = 30.0, poll_interval_sec: float = 0.1,
               "no summary produced", file=sys.stderr)
         return None
     eng = get_engine()
-    torch.cuda.current_stream(torch.device("cuda", eng.device)).synchronize()
+    # every stream of the device, torch's internal NCCL stream included: the native reduce issues
+    # its collectives on torch.distributed's own communicator, which must be idle by then (all ranks
+    # are here -- the rendezvous -- so whatever they had in flight completes)
+    torch.cuda.synchronize(torch.device("cuda", eng.device))
     comm = TorchDistComm() if distributed else LocalComm()
     res = SummaryEngine([eng], comm).build(window_rows or summary_window_rows(),
                                            window_rows or summary_window_rows())
