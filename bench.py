@@ -26,7 +26,8 @@ cross-rank reduce GB/s".  One invocation measures both legs:
 ``--impl reference`` runs the UNMODIFIED reference (``baseline/_ref``: ``pip install --target``
 of /root/reference, git-ignored, travels with the snapshot) in a separate process that maps none
 of this repository's native code: its own SQLite projection writers + its three summary
-sections on a bounded sample of the same workload (K timed steps, W warm-up), the default-window
+sections on a bounded sample of the same workload (K timed steps, W warm-up; the sample per step is
+sized from K so that the whole run costs ~100 s of reference time, never above --sample rows), the default-window
 line at full size, and the real ``traceml.trace_step`` overhead leg.  If ``baseline/_ref`` is
 missing it falls back to the oracle port and says so (``cpu_baseline.kind: "port"``).
 
