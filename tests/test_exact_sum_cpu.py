@@ -74,3 +74,80 @@ def test_python_loop_is_the_same_thing():
 def test_empty_and_zero_chains():
     assert xs(np.zeros(0))[0] == 0.0
     assert xs(np.zeros(5000)) == (0.0, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Executable specification of the walk's warp-wide map application (tml_exact_sum.cuh:
+# xs_apply_run).  The kernel applies 32 maps per step: lane i composes entries j..j+i by an
+# inclusive scan, applies that prefix to the running significand and the warp keeps the longest
+# prefix that stays inside the binade.  The GPU tests check the kernel's sums; this checks the
+# algorithm -- on Python integers, lane by lane -- against applying the entries one after the other.
+_ZERO = -2          # XS_PLAN_ZERO
+_INVALID = 2 ** 64 - 1
+
+
+def _apply_sequential(S, eb, f, e, j, end):
+    while j < end:
+        E = e[j]
+        if E == _ZERO:
+            j += 1
+            continue
+        if E != eb or E < 1:
+            break
+        c0, c1 = f[j]
+        S2 = S + (c1 if S & 1 else c0)
+        if c0 == _INVALID or (S2 >> 53):
+            break
+        S, j = S2, j + 1
+    return S, j
+
+
+def _compose(f, g):  # f first, then g (xs_compose_raw)
+    return (f[0] + (g[1] if f[0] & 1 else g[0]), f[1] + (g[1] if (1 + f[1]) & 1 else g[0]))
+
+
+def _apply_warp(S, eb, f, e, j, end):
+    while j < end:
+        maps, ok = [], []
+        for lane in range(32):
+            idx = j + lane
+            E, m = (e[idx], f[idx]) if idx < end else (_ZERO, (0, 0))
+            zero = E == _ZERO
+            ok.append(zero or (E == eb and 1 <= E < 0x7ff and m[0] != _INVALID))
+            maps.append((0, 0) if zero else m)
+        nvalid = next((i for i, o in enumerate(ok) if not o), 32)
+        maps = [m if i < nvalid else (0, 0) for i, m in enumerate(maps)]
+        d = 1
+        while d < 32:  # Hillis-Steele inclusive scan, ordered composition
+            maps = [_compose(maps[i - d], maps[i]) if i >= d else maps[i] for i in range(32)]
+            d *= 2
+        Si = [S + (p[1] if S & 1 else p[0]) for p in maps]
+        napply = min(next((i for i, s in enumerate(Si) if s >> 53), 32), nvalid)
+        if napply:
+            S = Si[napply - 1]
+        j += napply
+        if napply < 32:
+            break
+    return S, min(j, end)
+
+
+def test_warp_wide_application_equals_one_by_one():
+    import random
+
+    rnd = random.Random(7)
+    for _ in range(4000):
+        n, eb = rnd.randint(1, 100), rnd.choice([0, 5, 1000])
+        f, e = [], []
+        for _ in range(n):
+            r = rnd.random()
+            if r < 0.10:
+                e.append(_ZERO); f.append((7, 7))
+            elif r < 0.13:
+                e.append(rnd.choice([-1, -3, -10, eb + 1 if eb else 3])); f.append((1, 1))
+            elif r < 0.15:
+                e.append(eb); f.append((_INVALID, _INVALID))
+            else:
+                q = rnd.randint(0, 2 ** 50 if rnd.random() < 0.05 else 2 ** 40)
+                e.append(eb); f.append(rnd.choice([(q, q), (q + (q & 1), q + ((q + 1) & 1))]))
+        S, j0 = rnd.randint(2 ** 52, 2 ** 53 - 1), rnd.randint(0, n - 1)
+        assert _apply_sequential(S, eb, f, e, j0, n) == _apply_warp(S, eb, f, e, j0, n)
