@@ -151,3 +151,27 @@ def test_warp_wide_application_equals_one_by_one():
                 e.append(eb); f.append(rnd.choice([(q, q), (q + (q & 1), q + ((q + 1) & 1))]))
         S, j0 = rnd.randint(2 ** 52, 2 ** 53 - 1), rnd.randint(0, n - 1)
         assert _apply_sequential(S, eb, f, e, j0, n) == _apply_warp(S, eb, f, e, j0, n)
+
+
+def test_transposed_butterfly_totals_land_on_every_fourth_lane():
+    """K3a's chunk-sum reduction (tml_engine.cu, ``if (csum)``): 8 values per lane are folded
+    8 -> 4 -> 2 -> 1 while lanes pair up over bits 4, 3, 2, then two plain levels over bits 1, 0;
+    lane 4 j must end up with the total of value j over the 32 lanes (9 exchanges instead of 35)."""
+    rng = np.random.default_rng(0)
+    V = rng.integers(0, 1000, size=(32, 8)).astype(np.float64)
+    V[:, 7] = 0.0
+    lanes = np.arange(32)
+    v = V.copy()
+    for bit, width in ((16, 4), (8, 2), (4, 1)):
+        hi = (lanes & bit) != 0
+        nv = v.copy()
+        for i in range(width):
+            keep = np.where(hi, v[:, i + width], v[:, i])
+            send = np.where(hi, v[:, i], v[:, i + width])
+            nv[:, i] = keep + send[lanes ^ bit]
+        v = nv
+    t = v[:, 0]
+    t = t + t[lanes ^ 2]
+    t = t + t[lanes ^ 1]
+    for j in range(8):
+        assert t[4 * j] == V[:, j].sum()
